@@ -1,0 +1,103 @@
+/* probabilit_b200 -- C ABI of the B200-native sampling hot path of tommyod/probabilit.
+ *
+ * The reference is pure Python; its "plugin seam" is duck-typed:
+ *   correlator protocol   Correlator.set_target(C) -> self ; correlator(X) -> X'
+ *                         (reference src/probabilit/correlation.py:162-179, :368-425;
+ *                          called from src/probabilit/modeling.py:577-581)
+ * Each entry point below names the reference interface it replaces.  All functions return a
+ * pbl_status; pbl_last_error() gives the message of the last failure on the calling thread.
+ * Pointers named *_dev are device pointers on the current CUDA device, everything else is host
+ * memory.  Matrices are (n rows = observations, k columns = variables), fp64, addressed as
+ * base[row * row_stride + col * col_stride] with strides in ELEMENTS (NumPy F-order: row_stride 1,
+ * col_stride n; C-order: row_stride k, col_stride 1).  No call takes ownership of caller memory;
+ * inputs are never modified (the reference writes into np.empty_like(X), correlation.py:418).
+ */
+#ifndef PROBABILIT_B200_H
+#define PROBABILIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBL_API __attribute__((visibility("default")))
+
+typedef enum pbl_status {
+  PBL_OK = 0,
+  PBL_NOT_POSITIVE_DEFINITE = 1, /* ValueError "Rank data correlation not positive definite." correlation.py:399-403 */
+  PBL_NON_FINITE = 2,            /* ValueError "array must not contain infs or NaNs" (scipy check_finite at :409) */
+  PBL_BAD_SHAPE = 3,             /* ValueError from Correlator._validate_X, correlation.py:181-202 */
+  PBL_CUDA_ERROR = 4,
+  PBL_INTERNAL = 5
+} pbl_status;
+
+/* ---- library ---- */
+PBL_API int pbl_version(void);
+PBL_API const char* pbl_last_error(void);
+PBL_API int pbl_device_count(void);
+PBL_API int pbl_set_device(int device);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+PBL_API int64_t pbl_kernel_launches(void);
+
+/* ---- memory helpers (so that a host language without a CUDA binding can stage data) ---- */
+PBL_API int pbl_device_malloc(void** ptr_dev, uint64_t bytes);
+PBL_API int pbl_device_free(void* ptr_dev);
+PBL_API int pbl_host_malloc_pinned(void** ptr, uint64_t bytes);
+PBL_API int pbl_host_free_pinned(void* ptr);
+PBL_API int pbl_memcpy_h2d(void* dst_dev, const void* src, uint64_t bytes, void* stream);
+PBL_API int pbl_memcpy_d2h(void* dst, const void* src_dev, uint64_t bytes, void* stream);
+PBL_API int pbl_stream_synchronize(void* stream);
+
+/* ---- Iman-Conover correlator: ImanConover().set_target(C)(X), correlation.py:288-425 ---- */
+typedef struct pbl_ic_plan pbl_ic_plan;
+
+/* Workspace for (n, k) problems on the current device.  col_batch <= 0: choose automatically
+ * (columns sorted per launch batch; bounds the sort workspace). */
+PBL_API int pbl_ic_plan_create(int64_t n, int32_t k, int32_t col_batch, pbl_ic_plan** plan);
+PBL_API int pbl_ic_plan_destroy(pbl_ic_plan* plan);
+PBL_API uint64_t pbl_ic_plan_bytes(const pbl_ic_plan* plan);
+
+/* Correlator.set_target (correlation.py:162-179): the k x k validation and P = cholesky(C) stay
+ * on the host (NumPy); P_lower is that lower-triangular factor, row-major k*k doubles. */
+PBL_API int pbl_ic_plan_set_target(pbl_ic_plan* plan, const double* P_lower);
+
+/* ImanConover.__call__ (correlation.py:368-425) on device-resident X -> Y.  Synchronous: returns
+ * after the stream has drained, with the status the reference would have raised. */
+PBL_API int pbl_ic_plan_run(pbl_ic_plan* plan, const double* X_dev, int64_t x_row_stride,
+                    int64_t x_col_stride, double* Y_dev, int64_t y_row_stride,
+                    int64_t y_col_stride, void* stream);
+
+/* Same call with HOST buffers (what a NumPy caller holds): copies X to the device, runs, copies Y
+ * back.  X and Y must each be one contiguous block in C or F order. */
+PBL_API int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t x_row_stride,
+                         int64_t x_col_stride, const double* P_lower, double* Y,
+                         int64_t y_row_stride, int64_t y_col_stride);
+
+/* Stage-level entry points (asynchronous on `stream`): used by the parity tests and by the
+ * multi-GPU host driver, which places its collectives between them.
+ *   rank_scores : correlation.py:394-395 (+ np.sort of :423) for columns [col0, col0+ncols)
+ *   gram        : the reduction inside np.corrcoef, :398
+ *   solve       : corrcoef normalisation, cholesky, T = Q^-T P^T, :398-414 (n_total = global rows)
+ *   transform   : :409-414 applied to the rows
+ *   rank_gather : :419-423 for columns [col0, col0+ncols)
+ *   status      : synchronise and report (PBL_OK / NOT_POSITIVE_DEFINITE / NON_FINITE / ...)  */
+PBL_API int pbl_ic_stage_begin(pbl_ic_plan* plan, void* stream);
+PBL_API int pbl_ic_stage_rank_scores(pbl_ic_plan* plan, const double* X_dev, int64_t row_stride,
+                             int64_t col_stride, int32_t col0, int32_t ncols, void* stream);
+PBL_API int pbl_ic_stage_gram(pbl_ic_plan* plan, void* stream);
+PBL_API int pbl_ic_stage_solve(pbl_ic_plan* plan, int64_t n_total, void* stream);
+PBL_API int pbl_ic_stage_transform(pbl_ic_plan* plan, void* stream);
+PBL_API int pbl_ic_stage_rank_gather(pbl_ic_plan* plan, double* Y_dev, int64_t row_stride,
+                             int64_t col_stride, int32_t col0, int32_t ncols, void* stream);
+PBL_API int pbl_ic_stage_status(pbl_ic_plan* plan, void* stream);
+
+/* Device pointers to the plan's intermediates (column-major [k][n] unless noted), for parity
+ * tests and for collectives: what = 0 scores / correlated scores, 1 sortedX, 2 gram [k][k],
+ * 3 colsum [k], 4 T [k][k] row-major, 5 work (R then Q) [k][k]. */
+PBL_API int pbl_ic_plan_buffer(pbl_ic_plan* plan, int32_t what, void** ptr_dev, uint64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBABILIT_B200_H */

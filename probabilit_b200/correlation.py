@@ -1,0 +1,238 @@
+"""Correlators with the reference's interface, executing on the B200.
+
+Mirrors src/probabilit/correlation.py of the reference:
+
+* ``Correlator.set_target(C) -> self`` (:162-179) and ``_validate_X`` (:181-202) stay host NumPy
+  (k x k work; same checks, same exception types and messages);
+* ``ImanConover.__call__(X)`` (:368-425) runs the whole transform through the C ABI
+  (``pbl_ic_plan_*`` in include/probabilit_b200.h) -- there is no CPU path in this class.
+
+``X`` may be a NumPy array (host: copied to the device and back, like any NumPy caller of the
+reference would expect) or a CUDA ``torch.Tensor`` (device resident: no host traffic; the result
+is a tensor on the same device).  The class can be passed as ``correlator=`` to the modeling
+graph's ``sample`` exactly like the reference's own (modeling.py:505-507, :577-581).
+"""
+import abc
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class CorrelatorError(Exception):
+    pass
+
+
+def _is_positive_definite(X):
+    try:
+        np.linalg.cholesky(X)
+        return True
+    except np.linalg.LinAlgError:
+        return False
+
+
+class Correlator(abc.ABC):
+    def set_target(self, correlation_matrix):
+        """Set target correlation matrix (reference correlation.py:162-179)."""
+        if not isinstance(correlation_matrix, np.ndarray):
+            raise TypeError("Input argument `correlation_matrix` must be NumPy array.")
+        if not correlation_matrix.ndim == 2:
+            raise ValueError("Correlation matrix must be square.")
+        if not correlation_matrix.shape[0] == correlation_matrix.shape[1]:
+            raise ValueError("Correlation matrix must be square.")
+        if not np.allclose(np.diag(correlation_matrix), 1.0):
+            raise ValueError("Correlation matrix must have 1.0 on diagonal.")
+        if not np.allclose(correlation_matrix.T, correlation_matrix):
+            raise ValueError("Correlation matrix must be symmetric.")
+        if not _is_positive_definite(correlation_matrix):
+            raise ValueError("Correlation matrix must be positive definite.")
+
+        self.C = correlation_matrix.copy()
+        self.P = np.linalg.cholesky(self.C)
+        return self
+
+    def _validate_X(self, X, check_rows_cols=True):
+        """Validate array X of shape (observations, variables) (reference :181-202)."""
+        if not (hasattr(self, "C") and hasattr(self, "P")):
+            raise CorrelatorError("User must call `set_target` first.")
+        if not (isinstance(X, np.ndarray) or _is_cuda_tensor(X)):
+            raise TypeError("Input argument `X` must be NumPy array.")
+        if not X.ndim == 2:
+            raise ValueError("Correlation matrix must be square.")
+        N, K = X.shape
+        if self.P.shape[0] != K:
+            msg = f"Shape of `X` ({tuple(X.shape)}) does not match shape of "
+            msg += f"correlation matrix ({self.P.shape})"
+            raise ValueError(msg)
+        if check_rows_cols and N <= K:
+            msg = f"The matrix X must have rows > columns. Got shape: {tuple(X.shape)}"
+            raise ValueError(msg)
+        return N, K
+
+
+def _is_cuda_tensor(X):
+    return type(X).__module__.startswith("torch") and hasattr(X, "is_cuda") and X.is_cuda
+
+
+def _strides_elems(shape, strides_bytes, itemsize):
+    return tuple(s // itemsize for s in strides_bytes)
+
+
+class _IcPlan:
+    """Owns one pbl_ic_plan (device workspace for an (n, k) problem on one device)."""
+
+    def __init__(self, n, k, device, col_batch=0):
+        self.lib = _lib.require_gpu()
+        self.n, self.k, self.device = n, k, device
+        _lib.check(self.lib.pbl_set_device(device), "pbl_set_device")
+        h = C.c_void_p()
+        st = _lib.check(self.lib.pbl_ic_plan_create(n, k, col_batch, C.byref(h)), "pbl_ic_plan_create")
+        if st != _lib.STATUS_OK:
+            raise ValueError(_lib.last_error())
+        self.handle = h
+        self._P = None
+
+    def set_target(self, P):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        if self._P is not None and np.array_equal(P, self._P):
+            return
+        _lib.check(self.lib.pbl_ic_plan_set_target(self.handle, P.ctypes.data), "pbl_ic_plan_set_target")
+        self._P = P.copy()
+
+    def buffer(self, what):
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        _lib.check(self.lib.pbl_ic_plan_buffer(self.handle, what, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.pbl_ic_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_NOT_PD_MSG = (
+    "Rank data correlation not positive definite."
+    "There are perfect correlations in the ranked data."
+    "Supply more data (rows in X) or sample differently."
+)
+
+
+def _raise_for_status(st):
+    """Status of the device pipeline -> the exception the reference raises at that point."""
+    if st == _lib.STATUS_OK:
+        return
+    if st == _lib.STATUS_NOT_PD:
+        raise ValueError(_NOT_PD_MSG)  # correlation.py:399-403
+    if st == _lib.STATUS_NON_FINITE:
+        raise ValueError("array must not contain infs or NaNs")  # scipy check_finite at :409
+    raise ValueError(_lib.last_error())
+
+
+class ImanConover(Correlator):
+    """Iman-Conover transform on the GPU (reference correlation.py:288-425).
+
+    >>> transform = ImanConover().set_target(np.array([[1, 0.7], [0.7, 1]]))   # doctest: +SKIP
+    >>> X_transformed = transform(X)                                           # doctest: +SKIP
+    """
+
+    def __init__(self, device=None, col_batch=0):
+        self.device = device
+        self.col_batch = col_batch
+        self._plan = None
+        self._dev_bufs = None
+
+    def set_target(self, correlation_matrix):
+        super().set_target(correlation_matrix)
+        return self
+
+    # ------------------------------------------------------------------ plan management
+    def _get_plan(self, n, k, device):
+        p = self._plan
+        if p is None or (p.n, p.k, p.device) != (n, k, device):
+            if p is not None:
+                p.close()
+            self._free_dev_bufs()
+            p = self._plan = _IcPlan(n, k, device, self.col_batch)
+        p.set_target(self.P)
+        return p
+
+    def _free_dev_bufs(self):
+        if self._dev_bufs is not None:
+            lib = _lib.load()
+            for ptr in self._dev_bufs[:2]:
+                lib.pbl_device_free(C.c_void_p(ptr))
+            self._dev_bufs = None
+
+    def close(self):
+        """Release the device workspace."""
+        self._free_dev_bufs()
+        if self._plan is not None:
+            self._plan.close()
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ the transform
+    def __call__(self, X):
+        """Transform an input matrix X of shape (N, K); same contract as the reference's
+        ``ImanConover.__call__`` (correlation.py:368-425)."""
+        N, K = self._validate_X(X)
+        if _is_cuda_tensor(X):
+            return self._call_device(X, N, K)
+        return self._call_host(X, N, K)
+
+    def _call_host(self, X, N, K):
+        lib = _lib.require_gpu()
+        device = 0 if self.device is None else int(self.device)
+        Xd = X
+        if Xd.dtype != np.float64 or not (Xd.flags.f_contiguous or Xd.flags.c_contiguous):
+            Xd = np.asfortranarray(X, dtype=np.float64)
+        result = np.empty_like(Xd)  # correlation.py:418 (keeps the memory order of X)
+        plan = self._get_plan(N, K, device)
+        nbytes = Xd.nbytes
+        if self._dev_bufs is None or self._dev_bufs[2] != nbytes:
+            self._free_dev_bufs()
+            dX, dY = C.c_void_p(), C.c_void_p()
+            _lib.check(lib.pbl_device_malloc(C.byref(dX), nbytes), "pbl_device_malloc")
+            _lib.check(lib.pbl_device_malloc(C.byref(dY), nbytes), "pbl_device_malloc")
+            self._dev_bufs = (dX.value, dY.value, nbytes)
+        dX, dY, _ = self._dev_bufs
+        rs, cs = _strides_elems(Xd.shape, Xd.strides, 8)
+        yrs, ycs = _strides_elems(result.shape, result.strides, 8)
+        _lib.check(lib.pbl_memcpy_h2d(dX, Xd.ctypes.data, nbytes, None), "pbl_memcpy_h2d")
+        st = _lib.check(lib.pbl_ic_plan_run(plan.handle, dX, rs, cs, dY, yrs, ycs, None), "pbl_ic_plan_run")
+        _raise_for_status(st)
+        _lib.check(lib.pbl_memcpy_d2h(result.ctypes.data, dY, nbytes, None), "pbl_memcpy_d2h")
+        _lib.check(lib.pbl_stream_synchronize(None), "pbl_stream_synchronize")
+        if result.dtype != X.dtype:
+            result = result.astype(X.dtype)  # np.empty_like(X) keeps X's dtype in the reference
+        return result
+
+    def _call_device(self, X, N, K):
+        import torch
+
+        lib = _lib.require_gpu()
+        if X.dtype != torch.float64:
+            raise TypeError("device-resident X must be float64")
+        device = X.device.index if X.device.index is not None else torch.cuda.current_device()
+        plan = self._get_plan(N, K, device)
+        Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        st = _lib.check(
+            lib.pbl_ic_plan_run(plan.handle, X.data_ptr(), X.stride(0), X.stride(1), Y.data_ptr(),
+                                Y.stride(0), Y.stride(1), C.c_void_p(stream)),
+            "pbl_ic_plan_run",
+        )
+        _raise_for_status(st)
+        return Y

@@ -1,0 +1,186 @@
+// extern "C" boundary (include/probabilit_b200.h): plain pointers and sizes only.
+#include <atomic>
+#include <cstring>
+#include <string>
+
+#include "../../include/probabilit_b200.h"
+#include "common.cuh"
+#include "ic.cuh"
+
+namespace pbl {
+std::atomic<long long> g_kernel_launches{0};
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+}  // namespace pbl
+
+struct pbl_ic_plan {
+  pbl::IcPlan* impl;
+};
+
+using pbl::kBadShape;
+using pbl::kOk;
+
+extern "C" {
+
+int pbl_version(void) { return 100; }
+const char* pbl_last_error(void) { return pbl::get_last_error(); }
+
+int64_t pbl_kernel_launches(void) { return (int64_t)pbl::g_kernel_launches.load(); }
+
+int pbl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pbl_set_device(int device) {
+  PBL_CUDA_CHECK(cudaSetDevice(device));
+  return kOk;
+}
+
+int pbl_device_malloc(void** ptr, uint64_t bytes) {
+  PBL_CUDA_CHECK(cudaMalloc(ptr, bytes ? bytes : 16));
+  return kOk;
+}
+int pbl_device_free(void* ptr) {
+  PBL_CUDA_CHECK(cudaFree(ptr));
+  return kOk;
+}
+int pbl_host_malloc_pinned(void** ptr, uint64_t bytes) {
+  PBL_CUDA_CHECK(cudaMallocHost(ptr, bytes ? bytes : 16));
+  return kOk;
+}
+int pbl_host_free_pinned(void* ptr) {
+  PBL_CUDA_CHECK(cudaFreeHost(ptr));
+  return kOk;
+}
+int pbl_memcpy_h2d(void* dst, const void* src, uint64_t bytes, void* stream) {
+  PBL_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return kOk;
+}
+int pbl_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream) {
+  PBL_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return kOk;
+}
+int pbl_stream_synchronize(void* stream) {
+  PBL_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return kOk;
+}
+
+// ---------------------------------------------------------------------------- Iman-Conover
+int pbl_ic_plan_create(int64_t n, int32_t k, int32_t col_batch, pbl_ic_plan** plan) {
+  if (!plan) return kBadShape;
+  *plan = nullptr;
+  pbl::IcPlan* impl = nullptr;
+  PBL_RETURN_IF(pbl::ic_plan_create(n, k, col_batch, &impl));
+  *plan = new pbl_ic_plan{impl};
+  return kOk;
+}
+
+int pbl_ic_plan_destroy(pbl_ic_plan* plan) {
+  if (!plan) return kOk;
+  pbl::ic_plan_destroy(plan->impl);
+  delete plan;
+  return kOk;
+}
+
+uint64_t pbl_ic_plan_bytes(const pbl_ic_plan* plan) { return plan ? plan->impl->bytes : 0; }
+
+int pbl_ic_plan_set_target(pbl_ic_plan* plan, const double* P_lower) {
+  if (!plan || !P_lower) return kBadShape;
+  return pbl::ic_plan_set_target(plan->impl, P_lower);
+}
+
+int pbl_ic_plan_run(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, double* Y,
+                    int64_t yrs, int64_t ycs, void* stream) {
+  if (!plan || !X || !Y) return kBadShape;
+  if (!plan->impl->has_target) {
+    pbl::set_last_error("User must call `set_target` first.");
+    return kBadShape;
+  }
+  return pbl::ic_plan_run(plan->impl, X, xrs, xcs, Y, yrs, ycs, (cudaStream_t)stream);
+}
+
+static bool contiguous_layout(int64_t n, int32_t k, int64_t rs, int64_t cs) {
+  return (rs == 1 && cs == n) || (cs == 1 && rs == k) || (n == 1 && cs == 1) || (k == 1 && rs == 1);
+}
+
+int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t xrs, int64_t xcs,
+                         const double* P_lower, double* Y, int64_t yrs, int64_t ycs) {
+  if (!X || !Y || !P_lower) return kBadShape;
+  if (!contiguous_layout(n, k, xrs, xcs) || !contiguous_layout(n, k, yrs, ycs)) {
+    pbl::set_last_error("pbl_iman_conover_f64: X and Y must be contiguous in C or F order");
+    return kBadShape;
+  }
+  pbl_ic_plan* plan = nullptr;
+  double *dX = nullptr, *dY = nullptr;
+  const size_t bytes = (size_t)n * k * sizeof(double);
+  int rc = pbl_ic_plan_create(n, k, 0, &plan);
+  if (rc == kOk) rc = pbl_ic_plan_set_target(plan, P_lower);
+  if (rc == kOk && cudaMalloc((void**)&dX, bytes) != cudaSuccess) rc = pbl::kCudaError;
+  if (rc == kOk && cudaMalloc((void**)&dY, bytes) != cudaSuccess) rc = pbl::kCudaError;
+  if (rc == pbl::kCudaError && !*pbl::get_last_error()) pbl::set_last_error("cudaMalloc failed");
+  if (rc == kOk && cudaMemcpy(dX, X, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = pbl::kCudaError;
+  if (rc == kOk) rc = pbl_ic_plan_run(plan, dX, xrs, xcs, dY, yrs, ycs, nullptr);
+  if (rc == kOk && cudaMemcpy(Y, dY, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = pbl::kCudaError;
+  cudaFree(dX);
+  cudaFree(dY);
+  pbl_ic_plan_destroy(plan);
+  return rc;
+}
+
+int pbl_ic_stage_begin(pbl_ic_plan* plan, void* stream) {
+  if (!plan) return kBadShape;
+  PBL_CUDA_CHECK(cudaMemsetAsync(plan->impl->flags, 0, 8 * sizeof(uint32_t), (cudaStream_t)stream));
+  return kOk;
+}
+int pbl_ic_stage_rank_scores(pbl_ic_plan* plan, const double* X, int64_t rs, int64_t cs,
+                             int32_t col0, int32_t ncols, void* stream) {
+  if (!plan || !X || col0 < 0 || ncols < 0 || col0 + ncols > plan->impl->k) return kBadShape;
+  return pbl::ic_stage_rank_scores(plan->impl, X, rs, cs, col0, ncols, (cudaStream_t)stream);
+}
+int pbl_ic_stage_gram(pbl_ic_plan* plan, void* stream) {
+  if (!plan) return kBadShape;
+  return pbl::ic_stage_gram(plan->impl, (cudaStream_t)stream);
+}
+int pbl_ic_stage_solve(pbl_ic_plan* plan, int64_t n_total, void* stream) {
+  if (!plan) return kBadShape;
+  return pbl::ic_stage_solve(plan->impl, n_total, (cudaStream_t)stream);
+}
+int pbl_ic_stage_transform(pbl_ic_plan* plan, void* stream) {
+  if (!plan) return kBadShape;
+  return pbl::ic_stage_transform(plan->impl, (cudaStream_t)stream);
+}
+int pbl_ic_stage_rank_gather(pbl_ic_plan* plan, double* Y, int64_t rs, int64_t cs, int32_t col0,
+                             int32_t ncols, void* stream) {
+  if (!plan || !Y || col0 < 0 || ncols < 0 || col0 + ncols > plan->impl->k) return kBadShape;
+  return pbl::ic_stage_rank_gather(plan->impl, Y, rs, cs, col0, ncols, (cudaStream_t)stream);
+}
+int pbl_ic_stage_status(pbl_ic_plan* plan, void* stream) {
+  if (!plan) return kBadShape;
+  return pbl::ic_read_status(plan->impl, (cudaStream_t)stream);
+}
+
+int pbl_ic_plan_buffer(pbl_ic_plan* plan, int32_t what, void** ptr, uint64_t* bytes) {
+  if (!plan || !ptr) return kBadShape;
+  pbl::IcPlan* p = plan->impl;
+  const uint64_t nk = (uint64_t)p->n * p->k * 8, kk = (uint64_t)p->k * p->k * 8;
+  uint64_t b = 0;
+  switch (what) {
+    case 0: *ptr = p->scores; b = nk; break;
+    case 1: *ptr = p->sortedX; b = nk; break;
+    case 2: *ptr = p->gram; b = kk; break;
+    case 3: *ptr = p->colsum; b = (uint64_t)p->k * 8; break;
+    case 4: *ptr = p->T; b = kk; break;
+    case 5: *ptr = p->work; b = kk; break;
+    default: return kBadShape;
+  }
+  if (bytes) *bytes = b;
+  return kOk;
+}
+
+}  // extern "C"

@@ -1,0 +1,720 @@
+// Iman-Conover correlator on one B200 (reference: src/probabilit/correlation.py:368-425).
+//
+//   stage rank_scores  : per-column sort of X  -> tie-run average ranks -> van der Waerden scores
+//                        scattered back to row order, plus np.sort(X[:,c])      (:394-395, :423)
+//   stage gram         : fp64 Gram  S^T S  and column sums of the scores        (:398 np.corrcoef)
+//   stage solve        : corrcoef normalisation + clip, single-block Cholesky Q, T = Q^-T P^T
+//                                                                               (:398-414)
+//   stage transform    : correlated = scores @ T  (T upper triangular), in place (:409-414)
+//   stage rank_gather  : per-column sort of the correlated scores -> tie-run midpoint index
+//                        -> Y[row, c] = sortedX[c][index]                       (:419-423)
+//
+// Everything is column-major on the device ([k][n], one contiguous run per variable), which is
+// what the graph path hands over (np.vstack(...).T, reference src/probabilit/modeling.py:580).
+#include "ic.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ndtri.cuh"
+
+namespace pbl {
+
+namespace {
+
+// ======================================================================================
+// post-sort kernel: tie runs on the sorted column, then either scores (MODE 0) or the gather
+// of the sorted marginal (MODE 1)
+// ======================================================================================
+constexpr int kPostBlock = 256;
+constexpr int kPostItems = 8;
+constexpr int kPostTile = kPostBlock * kPostItems;
+
+__device__ __forceinline__ uint32_t block_excl_prefix_max(uint32_t v, uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= (uint32_t)d) incl = max(incl, t);
+  }
+  if (lane == 31) s_w[warp] = incl;
+  uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+  if (lane == 0) excl = 0;
+  __syncthreads();
+  for (uint32_t w = 0; w < warp; ++w) excl = max(excl, s_w[w]);
+  __syncthreads();
+  return excl;
+}
+
+__device__ __forceinline__ uint32_t block_excl_suffix_min(uint32_t v, uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_down_sync(0xFFFFFFFFu, incl, d);
+    if (lane + d < 32) incl = min(incl, t);
+  }
+  if (lane == 0) s_w[warp] = incl;
+  uint32_t excl = __shfl_down_sync(0xFFFFFFFFu, incl, 1);
+  if (lane == 31) excl = 0xFFFFFFFFu;
+  __syncthreads();
+  for (uint32_t w = warp + 1; w < kPostBlock / 32; ++w) excl = min(excl, s_w[w]);
+  __syncthreads();
+  return excl;
+}
+
+// MODE 0: out[col][row] = ndtri(average_rank / (n+1)),  sortedX[col][pos] = value
+//         (scipy.stats.rankdata 'average' + norm.ppf, correlation.py:394-395; np.sort, :423)
+// MODE 1: out[row, col] = sortedX[col][run_start + (run_len-1)/2]
+//         (rankdata(...).astype(int) - 1 then the gather, correlation.py:422-423)
+template <int MODE>
+__global__ void __launch_bounds__(kPostBlock)
+post_sort_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
+                 const uint32_t* __restrict__ valsA, const uint32_t* __restrict__ valsB,
+                 const PassPlan* __restrict__ plan, uint32_t n, double* __restrict__ sortedX,
+                 double* __restrict__ out, int64_t out_row_stride, int64_t out_col_stride) {
+  __shared__ double s_val[kPostTile + 2];
+  __shared__ uint32_t s_start[kPostTile];
+  __shared__ uint32_t s_end[kPostTile];
+  __shared__ uint32_t s_w[kPostBlock / 32];
+  __shared__ uint32_t s_lo, s_hi;
+
+  const int col = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int fb = plan[col].final_buf;
+  const uint64_t* keys = (fb == 1 ? keysA : keysB) + (size_t)col * n;
+  const uint32_t* rows = (fb == 1 ? valsA : valsB) + (size_t)col * n;
+  double* sx = sortedX + (size_t)col * n;
+  const uint32_t tile_start = blockIdx.x * (uint32_t)kPostTile;
+  const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
+
+  // values with a one-element halo on both sides; NaN outside the column (never ties)
+  for (uint32_t i = tid; i < nvalid + 2; i += kPostBlock) {
+    int64_t g = (int64_t)tile_start + i - 1;
+    double v = __longlong_as_double(0x7FF8000000000000LL);
+    if (g >= 0 && g < (int64_t)n) v = key_to_double(ld_stream_u64(keys + g));
+    s_val[i] = v;
+  }
+  __syncthreads();
+  int tie = 0;
+  for (uint32_t i = tid; i <= nvalid; i += kPostBlock) tie |= (s_val[i] == s_val[i + 1]);
+  tie = __syncthreads_or(tie);
+
+  if (tie) {
+    // blocked arrangement: thread t owns positions t*ITEMS .. t*ITEMS+ITEMS-1
+    uint32_t st[kPostItems], en[kPostItems];
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < kPostItems; ++i) {
+      uint32_t p = tid * kPostItems + i;
+      uint32_t v = 0;
+      if (p < nvalid && !(s_val[p] == s_val[p + 1])) v = tile_start + p + 1;  // head: pos+1
+      run = max(run, v);
+      st[i] = run;
+    }
+    uint32_t pre = block_excl_prefix_max(run, s_w);
+    run = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = kPostItems - 1; i >= 0; --i) {
+      uint32_t p = tid * kPostItems + i;
+      uint32_t v = 0xFFFFFFFFu;
+      if (p < nvalid && !(s_val[p + 1] == s_val[p + 2])) v = tile_start + p;  // tail: pos
+      run = min(run, v);
+      en[i] = run;
+    }
+    uint32_t suf = block_excl_suffix_min(run, s_w);
+    // runs that cross the tile boundary: binary search in the sorted column
+    if (tid == 0) {
+      uint32_t lo = tile_start, hi = tile_start + nvalid - 1;
+      if (s_val[0] == s_val[1]) {
+        double v = s_val[1];
+        uint32_t a = 0, b = tile_start;  // first q in [0, tile_start) with val[q] >= v
+        while (a < b) {
+          uint32_t mid = a + (b - a) / 2;
+          if (key_to_double(keys[mid]) < v) a = mid + 1; else b = mid;
+        }
+        lo = a;
+      }
+      if (s_val[nvalid] == s_val[nvalid + 1]) {
+        double v = s_val[nvalid];
+        uint32_t a = tile_start + nvalid, b = n;  // first q with val[q] > v
+        while (a < b) {
+          uint32_t mid = a + (b - a) / 2;
+          if (key_to_double(keys[mid]) > v) b = mid; else a = mid + 1;
+        }
+        hi = a - 1;
+      }
+      s_lo = lo;
+      s_hi = hi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPostItems; ++i) {
+      uint32_t p = tid * kPostItems + i;
+      if (p < nvalid) {
+        uint32_t s = max(st[i], pre);
+        uint32_t e = min(en[i], suf);
+        s_start[p] = (s == 0) ? s_lo : s - 1;
+        s_end[p] = (e == 0xFFFFFFFFu) ? s_hi : e;
+      }
+    }
+    __syncthreads();
+  }
+
+  double* outc = out + (int64_t)col * out_col_stride;
+#pragma unroll
+  for (int j = 0; j < kPostItems; ++j) {
+    uint32_t p = j * kPostBlock + tid;
+    if (p < nvalid) {
+      uint32_t g = tile_start + p;
+      uint32_t s = g, e = g;
+      if (tie) {
+        s = s_start[p];
+        e = s_end[p];
+      }
+      uint32_t row = ld_stream_u32(rows + g);
+      if (MODE == 0) {
+        double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
+        double q = __ddiv_rn(avg, (double)((uint64_t)n + 1ull));
+        outc[(int64_t)row * out_row_stride] = ndtri(q);
+        sx[g] = s_val[p + 1];
+      } else {
+        uint32_t m = s + (e - s) / 2;
+        outc[(int64_t)row * out_row_stride] = (m == g) ? sx[g] : sx[m];
+      }
+    }
+  }
+}
+
+// ======================================================================================
+// Gram: per (row block, column-tile pair) partial sums of s_i s_j and of s_i, then a fixed-order
+// reduction over row blocks (deterministic: no floating-point atomics).
+// Thread grid TG x TG, 4x4 outputs per thread, 256/TG^2 row groups per block.
+// ======================================================================================
+constexpr int kGramRows = 64;  // rows staged per step
+
+template <int TG>
+__global__ void __launch_bounds__(256)
+gram_kernel(const double* __restrict__ S, int64_t n, int k, double* __restrict__ partials,
+            int nrb, int64_t rows_per_block) {
+  constexpr int CT = 4 * TG;
+  constexpr int RG = 256 / (TG * TG);
+  constexpr int R = kGramRows;
+  constexpr int LD = R + 1;
+  extern __shared__ double gsm[];
+  double* sI = gsm;
+  double* sJ = gsm + CT * LD;
+
+  const int nt = (k + CT - 1) / CT;
+  int I = 0, J = 0;
+  {
+    int p = blockIdx.y;
+    for (I = 0; I < nt; ++I) {
+      int cnt = nt - I;
+      if (p < cnt) { J = I + p; break; }
+      p -= cnt;
+    }
+  }
+  const bool diag = (I == J);
+  if (diag) sJ = sI;
+  const int tid = threadIdx.x;
+  const int rg = tid / (TG * TG);
+  const int tt = tid % (TG * TG);
+  const int ti = tt / TG, tj = tt % TG;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(n, r_begin + rows_per_block);
+
+  double acc[4][4];
+  double sum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sum[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  }
+
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += R) {
+    for (int idx = tid; idx < CT * R; idx += 256) {
+      int c = idx / R, r = idx % R;
+      int64_t row = r0 + r;
+      int colI = I * CT + c;
+      sI[c * LD + r] = (colI < k && row < r_end) ? ld_stream_f64(S + (int64_t)colI * n + row) : 0.0;
+      if (!diag) {
+        int colJ = J * CT + c;
+        sJ[c * LD + r] = (colJ < k && row < r_end) ? ld_stream_f64(S + (int64_t)colJ * n + row) : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = rg; r < R; r += RG) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sI[(4 * ti + i) * LD + r];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sJ[(4 * tj + j) * LD + r];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      if (diag && tj == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sum[i] += a[i];
+      }
+    }
+    __syncthreads();
+  }
+
+  // fold the row groups in a fixed order
+  if (RG > 1) {
+    double* red = gsm;  // [TG*TG][20]
+    for (int g = 1; g < RG; ++g) {
+      if (rg == g) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) red[tt * 20 + i * 4 + j] = acc[i][j];
+          red[tt * 20 + 16 + i] = sum[i];
+        }
+      }
+      __syncthreads();
+      if (rg == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += red[tt * 20 + i * 4 + j];
+          sum[i] += red[tt * 20 + 16 + i];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (rg == 0) {
+    double* out = partials + ((size_t)blockIdx.y * nrb + blockIdx.x) * (CT * CT + CT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[(4 * ti + i) * CT + 4 * tj + j] = acc[i][j];
+      if (tj == 0) out[CT * CT + 4 * ti + i] = sum[i];
+    }
+  }
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ partials, int nrb, int k, int CT,
+                                   double* __restrict__ gram, double* __restrict__ colsum) {
+  const int nt = (k + CT - 1) / CT;
+  const int per = CT * CT + CT;
+  const int pair = blockIdx.y;
+  int I = 0, J = 0;
+  {
+    int p = pair;
+    for (I = 0; I < nt; ++I) {
+      int cnt = nt - I;
+      if (p < cnt) { J = I + p; break; }
+      p -= cnt;
+    }
+  }
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per) return;
+  double s = 0.0;
+  const double* src = partials + (size_t)pair * nrb * per + e;
+  for (int rb = 0; rb < nrb; ++rb) s += src[(size_t)rb * per];
+  if (e < CT * CT) {
+    int ci = I * CT + e / CT, cj = J * CT + e % CT;
+    if (ci < k && cj < k) {
+      gram[(size_t)ci * k + cj] = s;
+      if (I != J) gram[(size_t)cj * k + ci] = s;
+    }
+  } else if (I == J) {
+    int ci = I * CT + (e - CT * CT);
+    if (ci < k) colsum[ci] = s;
+  }
+}
+
+// ======================================================================================
+// single-block: np.corrcoef normalisation + clip, Cholesky (lower, in place in W),
+// T = Q^-T P^T (upper triangular).  numpy cov/corrcoef + np.linalg.cholesky +
+// solve_triangular(...) @ P.T of correlation.py:398-414, for the k x k part.
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsum,
+                  const double* __restrict__ P, double* __restrict__ W, double* __restrict__ T,
+                  int k, double n_total, uint32_t* __restrict__ flags) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const double inv = 1.0 / (n_total - 1.0);
+  for (int e = tid; e < k * k; e += nth) {
+    int i = e / k, j = e % k;
+    W[e] = (G[e] - colsum[i] * colsum[j] / n_total) * inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += nth) T[i] = sqrt(W[(size_t)i * k + i]);
+  __syncthreads();
+  for (int e = tid; e < k * k; e += nth) {
+    int i = e / k, j = e % k;
+    double c = W[e] / T[i];
+    c = c / T[j];
+    W[e] = fmin(fmax(c, -1.0), 1.0);  // NaN stays NaN only if both are NaN: checked below
+    if (c != c) W[e] = c;
+  }
+  __syncthreads();
+  // right-looking Cholesky, lower triangle
+  for (int j = 0; j < k; ++j) {
+    double d = W[(size_t)j * k + j];
+    if (!(d > 0.0)) {  // same acceptance as LAPACK dpotrf: pivot must be > 0 and not NaN
+      if (tid == 0) flags[2] = 1u;
+      // keep the rest of the pipeline well defined (its output is discarded by the caller)
+      for (int e = tid; e < k * k; e += nth) T[e] = 0.0;
+      return;
+    }
+    double q = sqrt(d);
+    __syncthreads();
+    for (int i = j + 1 + tid; i < k; i += nth) W[(size_t)i * k + j] /= q;
+    if (tid == 0) W[(size_t)j * k + j] = q;
+    __syncthreads();
+    const int t = k - j - 1;
+    for (int idx = tid; idx < t * t; idx += nth) {
+      int ii = idx / t, mm = idx % t;
+      if (mm <= ii) {
+        size_t i = j + 1 + ii, m = j + 1 + mm;
+        W[i * k + m] -= W[i * k + j] * W[m * k + j];
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution, one thread per column of T
+  for (int c = tid; c < k; c += nth) {
+    for (int i = k - 1; i >= 0; --i) {
+      if (i > c) {
+        T[(size_t)i * k + c] = 0.0;
+        continue;
+      }
+      double s = P[(size_t)c * k + i];
+      for (int m = i + 1; m <= c; ++m) s -= W[(size_t)m * k + i] * T[(size_t)m * k + c];
+      T[(size_t)i * k + c] = s / W[(size_t)i * k + i];
+    }
+  }
+}
+
+// ======================================================================================
+// transform: S <- S @ T in place, T upper triangular.
+// small k: one thread per row, the row lives in registers, T broadcast from shared memory.
+// ======================================================================================
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2)
+transform_small_kernel(double* __restrict__ S, int64_t n, int k, const double* __restrict__ T) {
+  __shared__ __align__(16) double sT[KMAX * KMAX];
+  for (int e = threadIdx.x; e < KMAX * KMAX; e += 256) {
+    int i = e / KMAX, j = e % KMAX;
+    sT[e] = (i < k && j < k) ? T[i * k + j] : 0.0;
+  }
+  __syncthreads();
+  // one row per thread (no row loop: keeps the T loads from being hoisted into registers)
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  // acc[c] = sum_{j<=c} s_j T[j][c], accumulated in increasing j; column j is final (and can
+  // overwrite its own input) as soon as row j of T has been applied.
+  double acc[KMAX];
+#pragma unroll
+  for (int c = 0; c < KMAX; ++c) acc[c] = 0.0;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < k) {
+      const double sj = S[(int64_t)j * n + r];
+#pragma unroll
+      for (int c = j; c < KMAX; ++c) acc[c] = fma(sj, sT[j * KMAX + c], acc[c]);
+      S[(int64_t)j * n + r] = acc[j];
+    }
+  }
+}
+
+// large k: 64-row x 64-column output tiles, 4x4 per thread, column tiles in descending order so
+// that the in-place update never overwrites an input it still needs.
+__global__ void __launch_bounds__(256)
+transform_tiled_kernel(double* __restrict__ S, int64_t n, int k, const double* __restrict__ T) {
+  constexpr int TS = 64;  // output tile edge
+  constexpr int JD = 32;  // depth staged per step
+  __shared__ __align__(16) double sS[JD * TS];  // [j][r]
+  __shared__ __align__(16) double sT[JD * TS];  // [j][c]
+  const int tid = threadIdx.x;
+  const int tr = tid % 16, tc = tid / 16;
+  const int64_t r0 = (int64_t)blockIdx.x * TS;
+  const int nt = (k + TS - 1) / TS;
+  for (int kt = nt - 1; kt >= 0; --kt) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int jmax = min(k, (kt + 1) * TS);  // T[j][c] = 0 for j > c
+    for (int j0 = 0; j0 < jmax; j0 += JD) {
+      for (int idx = tid; idx < JD * TS; idx += 256) {
+        int j = idx / TS, x = idx % TS;
+        int gj = j0 + j;
+        int64_t row = r0 + x;
+        sS[idx] = (gj < k && row < n) ? S[(int64_t)gj * n + row] : 0.0;
+        int gc = kt * TS + x;
+        sT[idx] = (gj < k && gc < k) ? T[(size_t)gj * k + gc] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int j = 0; j < JD; ++j) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sS[j * TS + 4 * tr + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = sT[j * TS + 4 * tc + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[i][c] = fma(a[i], b[c], acc[i][c]);
+      }
+      __syncthreads();
+    }
+    // all reads of this block's rows of column tile kt are complete (barrier above); lower
+    // column tiles never read tile kt again, so it can be overwritten now
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int gc = kt * TS + 4 * tc + c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int64_t row = r0 + 4 * tr + i;
+        if (gc < k && row < n) S[(int64_t)gc * n + row] = acc[i][c];
+      }
+    }
+  }
+}
+
+template <typename T_>
+int dev_alloc(T_** p, size_t count, IcPlan* plan) {
+  size_t bytes = std::max<size_t>(count * sizeof(T_), 16);
+  PBL_CUDA_CHECK(cudaMalloc((void**)p, bytes));
+  plan->bytes += bytes;
+  return kOk;
+}
+
+int gram_tg_for(int k) { return k <= 16 ? 4 : (k <= 32 ? 8 : 16); }
+
+}  // namespace
+
+// ======================================================================================
+// plan
+// ======================================================================================
+int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
+  *out = nullptr;
+  if (n < 1 || k < 1 || n > (int64_t)kMaxSortN || k > 8192) {
+    set_last_error("ic_plan_create: need 1 <= n < 2^30 and 1 <= k <= 8192");
+    return kBadShape;
+  }
+  IcPlan* p = new IcPlan();
+  p->n = n;
+  p->k = k;
+  PBL_CUDA_CHECK(cudaGetDevice(&p->device));
+  const char* lb = getenv("PBL_SORT_LOOKBACK");
+  p->use_lookback = !(lb && lb[0] == '0');
+
+  // column batch: as many columns per launch as fit in ~45% of free memory
+  size_t free_b = 0, total_b = 0;
+  PBL_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t fixed = (size_t)2 * k * n * 8;  // sortedX + scores
+  const size_t per_col = (size_t)n * 24 + sort_status_bytes(1, (uint32_t)n) + 16384;
+  if (col_batch <= 0) {
+    size_t budget = free_b > fixed ? (size_t)((free_b - fixed) * 0.6) : 0;
+    col_batch = (int)std::min<size_t>((size_t)k, std::max<size_t>(1, budget / per_col));
+  }
+  col_batch = std::max(1, std::min(col_batch, k));
+  p->col_batch = col_batch;
+  const int cb = col_batch;
+
+  int rc = kOk;
+  auto A = [&](auto** ptr, size_t count) {
+    if (rc == kOk) rc = dev_alloc(ptr, count, p);
+  };
+  A(&p->sort.keysA, (size_t)cb * n);
+  A(&p->sort.keysB, (size_t)cb * n);
+  A(&p->sort.valsA, (size_t)cb * n);
+  A(&p->sort.valsB, (size_t)cb * n);
+  A(&p->sort.hist, (size_t)cb * kNumPasses * kRadix);
+  A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
+  A(&p->sort.tile_counter, (size_t)cb * kNumPasses);
+  A(&p->sort.plan, (size_t)cb);
+  A(&p->flags, 8);
+  p->sort.error_flag = p->flags;
+  A(&p->sortedX, (size_t)k * n);
+  A(&p->scores, (size_t)k * n);
+  A(&p->gram, (size_t)k * k);
+  A(&p->colsum, (size_t)k);
+  A(&p->work, (size_t)k * k);
+  A(&p->T, (size_t)k * k);
+  A(&p->P, (size_t)k * k);
+
+  p->gram_tg = gram_tg_for(k);
+  const int CT = 4 * p->gram_tg;
+  const int nt = (k + CT - 1) / CT;
+  const int npairs = nt * (nt + 1) / 2;
+  int64_t max_rb = (n + kGramRows - 1) / kGramRows;
+  int want = std::max(1, (4 * num_sms() + npairs - 1) / npairs);
+  p->gram_row_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_rb, want));
+  A(&p->gram_partials, (size_t)npairs * p->gram_row_blocks * (CT * CT + CT));
+  if (rc != kOk) {
+    ic_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return kOk;
+}
+
+void ic_plan_destroy(IcPlan* p) {
+  if (!p) return;
+  cudaFree(p->sort.keysA);
+  cudaFree(p->sort.keysB);
+  cudaFree(p->sort.valsA);
+  cudaFree(p->sort.valsB);
+  cudaFree(p->sort.hist);
+  cudaFree(p->sort.status);
+  cudaFree(p->sort.tile_counter);
+  cudaFree(p->sort.plan);
+  cudaFree(p->flags);
+  cudaFree(p->sortedX);
+  cudaFree(p->scores);
+  cudaFree(p->gram);
+  cudaFree(p->colsum);
+  cudaFree(p->work);
+  cudaFree(p->T);
+  cudaFree(p->P);
+  cudaFree(p->gram_partials);
+  delete p;
+}
+
+int ic_plan_set_target(IcPlan* p, const double* P_lower_host) {
+  PBL_CUDA_CHECK(cudaMemcpy(p->P, P_lower_host, (size_t)p->k * p->k * 8, cudaMemcpyHostToDevice));
+  p->has_target = true;
+  return kOk;
+}
+
+// ======================================================================================
+// stages
+// ======================================================================================
+static SortBuffers sort_view(const IcPlan* p) { return p->sort; }
+
+int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
+                         int col0, int ncols, cudaStream_t stream) {
+  const uint32_t n = (uint32_t)p->n;
+  for (int c = col0; c < col0 + ncols; c += p->col_batch) {
+    int nb = std::min(p->col_batch, col0 + ncols - c);
+    PBL_RETURN_IF(sort_columns_f64(X + (int64_t)c * col_stride, row_stride, col_stride, n, nb,
+                                   sort_view(p), p->use_lookback, stream));
+    dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
+    post_sort_kernel<0><<<grid, kPostBlock, 0, stream>>>(
+        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, n,
+        p->sortedX + (size_t)c * n, p->scores + (size_t)c * n, 1, (int64_t)n);
+    PBL_LAUNCH_CHECK();
+  }
+  return kOk;
+}
+
+int ic_stage_gram(IcPlan* p, cudaStream_t stream) {
+  const int TG = p->gram_tg, CT = 4 * TG;
+  const int nt = (p->k + CT - 1) / CT;
+  const int npairs = nt * (nt + 1) / 2;
+  const int nrb = p->gram_row_blocks;
+  int64_t rows_per = (p->n + nrb - 1) / nrb;
+  rows_per = (rows_per + kGramRows - 1) / kGramRows * kGramRows;
+  dim3 grid((unsigned)nrb, (unsigned)npairs);
+  size_t smem = (size_t)2 * CT * (kGramRows + 1) * 8;
+  smem = std::max(smem, (size_t)TG * TG * 20 * 8);
+  if (TG == 4)
+    gram_kernel<4><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
+  else if (TG == 8)
+    gram_kernel<8><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      PBL_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    gram_kernel<16><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
+  }
+  PBL_LAUNCH_CHECK();
+  const int per = CT * CT + CT;
+  gram_reduce_kernel<<<dim3((per + 255) / 256, npairs), 256, 0, stream>>>(
+      p->gram_partials, nrb, p->k, CT, p->gram, p->colsum);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int ic_stage_solve(IcPlan* p, int64_t n_total, cudaStream_t stream) {
+  if (!p->has_target) {
+    set_last_error("ic: set_target has not been called");
+    return kBadShape;
+  }
+  chol_solve_kernel<<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, p->k,
+                                          (double)n_total, p->flags);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int ic_stage_transform(IcPlan* p, cudaStream_t stream) {
+  const int k = p->k;
+  const int64_t n = p->n;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (k <= 8)
+    transform_small_kernel<8><<<blocks, 256, 0, stream>>>(p->scores, n, k, p->T);
+  else if (k <= 16)
+    transform_small_kernel<16><<<blocks, 256, 0, stream>>>(p->scores, n, k, p->T);
+  else if (k <= 32)
+    transform_small_kernel<32><<<blocks, 256, 0, stream>>>(p->scores, n, k, p->T);
+  else
+    transform_tiled_kernel<<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(p->scores, n, k, p->T);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_stride, int col0,
+                         int ncols, cudaStream_t stream) {
+  const uint32_t n = (uint32_t)p->n;
+  for (int c = col0; c < col0 + ncols; c += p->col_batch) {
+    int nb = std::min(p->col_batch, col0 + ncols - c);
+    PBL_RETURN_IF(sort_columns_f64(p->scores + (size_t)c * n, 1, (int64_t)n, n, nb, sort_view(p),
+                                   p->use_lookback, stream));
+    dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
+    post_sort_kernel<1><<<grid, kPostBlock, 0, stream>>>(
+        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, n,
+        p->sortedX + (size_t)c * n, Y + (int64_t)c * col_stride, row_stride, col_stride);
+    PBL_LAUNCH_CHECK();
+  }
+  return kOk;
+}
+
+int ic_read_status(IcPlan* p, cudaStream_t stream) {
+  uint32_t h[8];
+  PBL_CUDA_CHECK(cudaMemcpyAsync(h, p->flags, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  PBL_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (h[0]) {
+    set_last_error("radix sort look-back watchdog fired (internal error)");
+    return kInternal;
+  }
+  if (h[1]) {
+    set_last_error("array must not contain infs or NaNs");
+    return kNonFinite;
+  }
+  if (h[2]) {
+    set_last_error("Rank data correlation not positive definite.");
+    return kNotPositiveDefinite;
+  }
+  return kOk;
+}
+
+int ic_plan_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, double* Y, int64_t yrs,
+                int64_t ycs, cudaStream_t stream) {
+  PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
+  PBL_RETURN_IF(ic_stage_rank_scores(p, X, xrs, xcs, 0, p->k, stream));
+  PBL_RETURN_IF(ic_stage_gram(p, stream));
+  PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
+  PBL_RETURN_IF(ic_stage_transform(p, stream));
+  PBL_RETURN_IF(ic_stage_rank_gather(p, Y, yrs, ycs, 0, p->k, stream));
+  return ic_read_status(p, stream);
+}
+
+}  // namespace pbl

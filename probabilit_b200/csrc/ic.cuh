@@ -1,0 +1,53 @@
+// Iman-Conover on the device: plan object + stage entry points (internal C++ API; the C ABI
+// in capi.cu is a thin wrapper).  Reference: src/probabilit/correlation.py:368-425.
+#pragma once
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace pbl {
+
+struct IcPlan {
+  int device = 0;
+  int64_t n = 0;       // rows (observations)
+  int k = 0;           // columns (variables)
+  int col_batch = 0;   // columns sorted per launch batch (bounds the sort workspace)
+  bool use_lookback = true;
+  bool has_target = false;
+
+  SortBuffers sort;            // sized for col_batch columns
+  double* sortedX = nullptr;   // [k][n]  np.sort(X[:,c])
+  double* scores = nullptr;    // [k][n]  van der Waerden scores, then (in place) correlated scores
+  double* gram_partials = nullptr;
+  int gram_row_blocks = 0;
+  int gram_tg = 0;             // thread-grid edge of the Gram kernel (4, 8 or 16)
+  double* gram = nullptr;      // [k][k] sum_r s_ri s_rj
+  double* colsum = nullptr;    // [k]
+  double* work = nullptr;      // [k][k] scratch: R, then Q (lower Cholesky factor)
+  double* T = nullptr;         // [k][k] row-major, upper triangular: correlated = scores @ T
+  double* P = nullptr;         // [k][k] row-major lower Cholesky factor of the target C
+  uint32_t* flags = nullptr;   // [8]: 0 look-back watchdog, 1 NaN in X, 2 not PD, 3 non-finite scores
+  size_t bytes = 0;            // device bytes held by the plan
+};
+
+int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out);
+void ic_plan_destroy(IcPlan* plan);
+int ic_plan_set_target(IcPlan* plan, const double* P_lower_host);
+
+// Full transform on device-resident data.  X and Y are (n, k) with the given element strides
+// (F-order: row_stride 1, col_stride n).  Synchronises the stream before returning (the reference
+// call is synchronous and the status has to come back).
+int ic_plan_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
+                double* Y, int64_t y_row_stride, int64_t y_col_stride, cudaStream_t stream);
+
+// Stage-level entry points (parity tests, and the multi-GPU host driver which interleaves
+// collectives between them).  All asynchronous on `stream`.
+int ic_stage_rank_scores(IcPlan* plan, const double* X, int64_t row_stride, int64_t col_stride,
+                         int col0, int ncols, cudaStream_t stream);
+int ic_stage_gram(IcPlan* plan, cudaStream_t stream);
+int ic_stage_solve(IcPlan* plan, int64_t n_total, cudaStream_t stream);
+int ic_stage_transform(IcPlan* plan, cudaStream_t stream);
+int ic_stage_rank_gather(IcPlan* plan, double* Y, int64_t row_stride, int64_t col_stride,
+                         int col0, int ncols, cudaStream_t stream);
+int ic_read_status(IcPlan* plan, cudaStream_t stream);
+
+}  // namespace pbl

@@ -1,0 +1,183 @@
+"""Parity of the CUDA Iman-Conover path (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Bar: output bit-exact (it is a per-column re-ordering of the input),
+rank indices identical, scores within 4 ulp of scipy's norm.ppf, R/T to 1e-12."""
+import numpy as np
+import pytest
+import scipy as sp
+import scipy.stats
+
+from conftest import random_target
+from oracle import iman_conover as oic
+
+import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["readme_lhs", "toy_ties", "normal_1000x2", "lognormal_1000x2", "sobol_mixed_4096x16",
+         "poisson_2000x3", "specials_500x4", "wide_700x64"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_output_equals_reference_golden(ic_golden, name):
+    from probabilit_b200 import ImanConover
+
+    X, C, Y = ic_golden[name]
+    got = ImanConover().set_target(C)(X)
+    assert got.dtype == Y.dtype and got.shape == Y.shape
+    assert got.flags.f_contiguous == Y.flags.f_contiguous
+    np.testing.assert_array_equal(got, Y)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stages_against_oracle(ic_golden, name):
+    X, C, Y = ic_golden[name]
+    ref = oic.iman_conover_stages(X, C)
+    got = gpu_util.run_stages(X, C)
+    assert got["status"] == 0
+    np.testing.assert_array_equal(got["sortedX"], ref["sortedX"])
+    ulp = gpu_util.ulp_diff(got["scores"], ref["scores"])
+    assert ulp.max() <= 4, f"scores differ by {ulp.max()} ulp"
+    N = X.shape[0]
+    np.testing.assert_allclose(got["gram"], ref["scores"].T @ ref["scores"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(got["colsum"], ref["scores"].sum(axis=0), rtol=0, atol=1e-9 * N ** 0.5)
+    np.testing.assert_allclose(got["Q"], ref["Q"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got["T"], ref["T"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got["correlated"], ref["correlated"], rtol=0, atol=1e-10)
+    np.testing.assert_array_equal(got["result"], Y)
+
+
+@pytest.mark.parametrize("lookback", ["1", "0"])
+@pytest.mark.parametrize("n,k,seed", [(100_000, 5, 0), (300_001, 3, 1), (4097, 7, 2), (65_536, 16, 3)])
+def test_random_problems_bit_exact(monkeypatch, n, k, seed, lookback):
+    """Multi-tile sorts (look-back across tiles) with and without the look-back path."""
+    from probabilit_b200 import ImanConover
+
+    monkeypatch.setenv("PBL_SORT_LOOKBACK", lookback)
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.normal(size=(n, k)) * rng.lognormal(size=k) + rng.normal(size=k))
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got = ImanConover().set_target(C)(X)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_heavy_ties_multi_tile():
+    """Tie runs that span many tiles (binary-search path of the post-sort kernel)."""
+    from probabilit_b200 import ImanConover
+
+    rng = np.random.default_rng(7)
+    n, k = 50_000, 4
+    X = np.empty((n, k), order="F")
+    X[:, 0] = rng.poisson(2.0, n)
+    X[:, 1] = rng.integers(0, 3, n)
+    X[:, 2] = np.round(rng.normal(size=n), 2)
+    X[:, 3] = rng.normal(size=n)
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got = ImanConover().set_target(C)(X)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_c_order_and_column_batches():
+    from probabilit_b200 import ImanConover
+
+    rng = np.random.default_rng(11)
+    X = np.ascontiguousarray(rng.normal(size=(20_000, 6)))
+    C = random_target(rng, 6)
+    want = oic.iman_conover(X, C)
+    got = ImanConover(col_batch=4).set_target(C)(X)
+    assert got.flags.c_contiguous
+    np.testing.assert_array_equal(got, want)
+
+
+def test_one_shot_c_entry_point(ic_golden):
+    """pbl_iman_conover_f64: the single C call a foreign host would bind."""
+    from probabilit_b200 import _lib
+
+    lib = _lib.require_gpu()
+    X, C, Y = ic_golden["sobol_mixed_4096x16"]
+    P = np.ascontiguousarray(np.linalg.cholesky(C))
+    out = np.empty_like(X)
+    rs, cs = (s // 8 for s in X.strides)
+    st = lib.pbl_iman_conover_f64(X.ctypes.data, X.shape[0], X.shape[1], rs, cs, P.ctypes.data,
+                                  out.ctypes.data, rs, cs)
+    assert st == 0, _lib.last_error()
+    np.testing.assert_array_equal(out, Y)
+
+
+def test_error_conventions():
+    """Same exception types as the reference (tests/test_iman_conover.py:49-109, :200-210)."""
+    from probabilit_b200 import CorrelatorError, ImanConover
+
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(100, 3))
+    with pytest.raises(ValueError):
+        ImanConover().set_target(np.array([[1.0, 0.7, -0.3], [0.8, 1.0, 0.5], [-0.3, 0.5, 1.0]]))(X)
+    with pytest.raises(ValueError):
+        ImanConover().set_target(np.array([[1.0, 2.0, 0.3], [2.0, 1.0, 0.2], [0.3, 0.2, 1.0]]))(X)
+    with pytest.raises(ValueError):
+        ImanConover().set_target(np.array([[1.0, 0.5], [0.5, 1.0]]))(X)
+    with pytest.raises(ValueError, match="not positive definite"):
+        ImanConover().set_target(np.identity(2))(np.array([[1.0, 1], [2.0, 1.1], [2.1, 3]]))
+    with pytest.raises(CorrelatorError):
+        ImanConover()(X)
+    with pytest.raises(TypeError):
+        ImanConover().set_target(np.identity(3))([[1.0, 2.0, 3.0]])
+    Xn = X.copy()
+    Xn[3, 1] = np.nan
+    with pytest.raises(ValueError, match="infs or NaNs"):
+        ImanConover().set_target(np.identity(3))(Xn)
+    with pytest.raises(ValueError):  # rows <= columns
+        ImanConover().set_target(np.identity(3))(X[:3])
+
+
+def test_reference_property_tests():
+    """Ports of tests/test_iman_conover.py:33-46 and :146-176 (marginals, Spearman, distance)."""
+    from probabilit_b200 import ImanConover
+
+    for seed in range(10):
+        rng = np.random.default_rng(seed)
+        n_variables = int(rng.integers(2, 100))
+        n_observations = n_variables * 10
+        desired = random_target(rng, n_variables)
+        X = rng.normal(size=(n_observations, n_variables))
+        Xt = ImanConover().set_target(desired)(X)
+        for j in range(n_variables):
+            np.testing.assert_array_equal(np.sort(X[:, j]), np.sort(Xt[:, j]))
+        before = sp.linalg.norm(np.corrcoef(X, rowvar=False) - desired, ord="fro")
+        after = sp.linalg.norm(np.corrcoef(Xt, rowvar=False) - desired, ord="fro")
+        assert after <= before
+
+
+def test_device_resident_tensor_path():
+    torch = pytest.importorskip("torch")
+    from probabilit_b200 import ImanConover
+
+    rng = np.random.default_rng(3)
+    X = np.asfortranarray(rng.normal(size=(30_000, 8)))
+    C = random_target(rng, 8)
+    want = oic.iman_conover(X, C)
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().T  # (n, k) view, column-major
+    assert Xd.stride() == (1, X.shape[0])
+    Yd = ImanConover().set_target(C)(Xd)
+    assert Yd.is_cuda and Yd.stride() == Xd.stride()
+    np.testing.assert_array_equal(Yd.cpu().numpy(), want)
+
+
+def test_large_n_invariants():
+    """N = 2^24 rows, d = 4: too big for the oracle in seconds on every column, so check the
+    size-independent properties: per-column permutation (sorted columns identical), column 0
+    unchanged (T[0,0] > 0), Spearman close to target, and the oracle on one column."""
+    torch = pytest.importorskip("torch")
+    from probabilit_b200 import ImanConover
+
+    n, k = 1 << 24, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Xd = torch.randn((k, n), generator=g, device="cuda", dtype=torch.float64).T
+    rng = np.random.default_rng(0)
+    C = random_target(rng, k)
+    Yd = ImanConover().set_target(C)(Xd)
+    assert torch.equal(torch.sort(Xd, dim=0).values, torch.sort(Yd, dim=0).values)
+    assert torch.equal(Xd[:, 0], Yd[:, 0])
+    R = torch.corrcoef(Yd.T).cpu().numpy()
+    assert np.abs(R - C).max() < 0.01
