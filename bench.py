@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: Iman-Conover samples*vars/s (fp64, N=1e8 rows per GPU, d=16).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference's CPU path (oracle port) on the host
+
+A step = one ImanConover.__call__-equivalent over one (N, d) batch of synthetic input:
+  value  device-resident (inputs already in HBM), CUDA events on the launching stream
+  e2e    the public API call ImanConover().set_target(C)(X) with HOST (pinned) buffers, the
+         host->device and device->host copies inside the timed region
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "iman_conover_samples_vars_per_s"
+UNIT = "samples*vars/s"
+IC_BYTES_PER_SAMPLE_VAR = 456.0  # fixed algorithmic accounting
+PASS_BYTES_PER_KEY = (7 * 24.0 + 20.0) / 8.0  # 12 B in + 12 B out per key and digit pass; pass 0 reads 8 B
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def target_matrix(d):
+    """Recipe of the reference's tests/test_iman_conover.py:154-155, seed 0."""
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(2 * d, d))
+    return 0.9 * np.corrcoef(A, rowvar=False) + 0.1 * np.eye(d)
+
+
+def make_workload_device(n, d, seed, torch):
+    """(n, d) fp64, column-major on the device: marginals cycling norm(1,2) / triang(0.5) /
+    gamma(a=2) by column (config 3 of BASELINE.json), from pseudo-random uniforms."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.empty((d, n), dtype=torch.float64, device="cuda")
+    for c in range(d):
+        u = torch.rand(n, generator=g, dtype=torch.float64, device="cuda")
+        u.clamp_(1e-300, 1 - 1e-16)
+        if c % 3 == 0:
+            X[c] = 1.0 + 2.0 * torch.special.ndtri(u)
+        elif c % 3 == 1:
+            X[c] = torch.where(u < 0.5, torch.sqrt(0.5 * u), 1.0 - torch.sqrt(0.5 * (1.0 - u)))
+        else:
+            u2 = torch.rand(n, generator=g, dtype=torch.float64, device="cuda").clamp_(1e-300, 1.0)
+            X[c] = -torch.log(u) - torch.log(u2)  # gamma(a=2) as a sum of two exponentials
+            del u2
+        del u
+    return X.T  # (n, d) view with strides (1, n)
+
+
+def make_workload_host(n, d, seed):
+    """Same marginals on the host (NumPy/SciPy), for the CPU arm."""
+    import scipy.stats as st
+
+    rng = np.random.default_rng(seed)
+    X = np.empty((n, d), order="F")
+    for c in range(d):
+        u = rng.random(n)
+        if c % 3 == 0:
+            X[:, c] = st.norm(loc=1, scale=2).ppf(u)
+        elif c % 3 == 1:
+            X[:, c] = st.triang(0.5).ppf(u)
+        else:
+            X[:, c] = st.gamma(a=2).ppf(u)
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smmax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smmax)) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_cpu_port(n_rows, d, reps=1):
+    """The reference's CPU path (oracle port: same SciPy/NumPy calls, oracle/iman_conover.py)."""
+    from oracle import iman_conover as oic
+
+    X = make_workload_host(n_rows, d, seed=1)
+    Ct = target_matrix(d)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oic.iman_conover(X, Ct)
+        best = min(best, time.perf_counter() - t0)
+    return n_rows * d / best, best
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_ref, d = args.ref_rows, args.d
+    from oracle import iman_conover as oic
+
+    X = make_workload_host(n_ref, d, seed=1)
+    Ct = target_matrix(d)
+    for _ in range(args.warmup):
+        oic.iman_conover(X, Ct)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oic.iman_conover(X, Ct)
+    dt = time.perf_counter() - t0
+    value = n_ref * d * args.steps / dt
+    sample = (f"{n_ref} of the {args.n} rows x d={d} per step (the full N needs ~150 GB of host RAM in "
+              "the reference); same marginals and target as the GPU arm")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Iman-Conover fp64 N={args.n} d={d} mixed norm/triang/gamma marginals "
+                               "(BASELINE.json configs[2])", "cpu_rows_per_step": n_ref},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    from probabilit_b200 import ImanConover, _lib
+    from probabilit_b200.correlation import _IcPlan
+
+    lib = _lib.require_gpu()  # raises without the CUDA library / a GPU: no fallback
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, d = args.n, args.d
+    Ct = target_matrix(d)
+    X = make_workload_device(n, d, seed=1234 + rank, torch=torch)
+    Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    if world > 1:
+        from probabilit_b200.distributed import DistributedImanConover
+        runner = DistributedImanConover(n, d, Ct, dist)
+        step = lambda: runner.run(X, Y)  # noqa: E731
+    else:
+        plan = _IcPlan(n, d, local_rank, args.col_batch)
+        plan.set_target(np.linalg.cholesky(Ct))
+
+        def step():
+            st = lib.pbl_ic_plan_run(plan.handle, X.data_ptr(), X.stride(0), X.stride(1),
+                                     Y.data_ptr(), Y.stride(0), Y.stride(1), sp)
+            if st != 0:
+                raise RuntimeError(f"pbl_ic_plan_run status {st}: {_lib.last_error()}")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.pbl_sort_profile_enable(1)
+    launches0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches() - launches0
+    nl, pms, nkeys = C.c_int64(), C.c_double(), C.c_int64()
+    lib.pbl_sort_profile_read(C.byref(nl), C.byref(pms), C.byref(nkeys))
+    lib.pbl_sort_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = float(n) * d * world * args.steps / (ms * 1e-3)
+
+    # parity guard inside the bench: Y is a per-column permutation of X (column 0 untouched)
+    if not torch.equal(X[:, 0], Y[:, 0]) and world == 1:
+        raise RuntimeError("bench: column 0 changed -- the transform is broken")
+
+    # ---- e2e through the public API with host (pinned) buffers ----
+    e2e = None
+    if world == 1 and args.e2e_steps > 0:
+        nbytes = n * d * 8
+        hx, hy = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hx), nbytes))
+        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hy), nbytes))
+        Xh = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(d, n)).T
+        Yh = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_double)), shape=(d, n)).T
+        _lib.check(lib.pbl_memcpy_d2h(hx, C.c_void_p(X.data_ptr()), nbytes, None))
+        _lib.check(lib.pbl_stream_synchronize(None))
+        plan.close()  # the public-API object below owns its own workspace
+        torch.cuda.synchronize()
+        ic = ImanConover(device=local_rank, col_batch=args.col_batch).set_target(Ct)
+        ic(Xh, out=Yh)  # warm-up (allocates the device workspace)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ic(Xh, out=Yh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if not np.array_equal(Xh[:1000, 0], Yh[:1000, 0]):
+            raise RuntimeError("bench e2e: column 0 changed")
+        e2e = {"value": float(n) * d * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "probabilit_b200.ImanConover().set_target(C)(X_host, out=Y_host_pinned)"}
+        ic.close()
+        lib.pbl_host_free_pinned(hx)
+        lib.pbl_host_free_pinned(hy)
+
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    pass_gbs = PASS_BYTES_PER_KEY * nkeys.value / (pms.value * 1e-3) / 1e9 if pms.value > 0 else None
+    roofline = {
+        "kernel": "onesweep_pass_kernel (one radix digit pass over all columns)",
+        "bound": "hbm", "achieved": pass_gbs, "peak": peak, "unit": "GB/s",
+        "frac": (pass_gbs / peak) if pass_gbs else None, "traffic": None,
+        "peak_source": peak_src,
+        "launches_timed": nl.value, "avg_launch_ms": (pms.value / nl.value) if nl.value else None,
+        "algorithmic_bytes_per_launch": PASS_BYTES_PER_KEY * nkeys.value / max(nl.value, 1),
+        "share_of_step": pms.value / ms if ms > 0 else None,
+        "pipeline": {"algorithmic_bytes_per_sample_var": IC_BYTES_PER_SAMPLE_VAR,
+                     "achieved": IC_BYTES_PER_SAMPLE_VAR * value / world / 1e9,
+                     "frac": IC_BYTES_PER_SAMPLE_VAR * value / world / 1e9 / peak},
+    }
+    cpu = None
+    if world == 1 and args.cpu_rows > 0:
+        v, secs = time_cpu_port(args.cpu_rows, d)
+        cpu = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "seconds": secs,
+               "sample": f"first-principles same workload at {args.cpu_rows} rows x d={d} (1 run); "
+                         "sorts/ndtri are single-threaded NumPy/SciPy, only BLAS uses the threads"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Iman-Conover fp64 N={n} rows per GPU, d={d}, mixed norm/triang/gamma "
+                               "marginals (BASELINE.json configs[2]), pseudo-random uniforms",
+                   "rows_per_gpu": n, "d": d, "l2": "inputs (12.8 GB) far exceed the 126 MB L2",
+                   "col_batch": args.col_batch},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=lambda s: int(float(s)), default=100_000_000)
+    ap.add_argument("--d", type=int, default=16)
+    ap.add_argument("--col-batch", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-rows", type=lambda s: int(float(s)), default=3_000_000)
+    ap.add_argument("--ref-rows", type=lambda s: int(float(s)), default=1_000_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,11 @@ PBL_API int pbl_set_device(int device);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 PBL_API int64_t pbl_kernel_launches(void);
 
+/* CUDA-event timing of the radix-sort digit passes (the dominant kernel), for bench.py's
+ * roofline leg: enable, run, then read (#launches, their total ms, keys moved) and reset. */
+PBL_API int pbl_sort_profile_enable(int on);
+PBL_API int pbl_sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys);
+
 /* ---- memory helpers (so that a host language without a CUDA binding can stage data) ---- */
 PBL_API int pbl_device_malloc(void** ptr_dev, uint64_t bytes);
 PBL_API int pbl_device_free(void* ptr_dev);

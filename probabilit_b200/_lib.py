@@ -29,6 +29,8 @@ SIGNATURES = {
     "pbl_device_count": (C.c_int, []),
     "pbl_set_device": (C.c_int, [C.c_int]),
     "pbl_kernel_launches": (_i64, []),
+    "pbl_sort_profile_enable": (C.c_int, [C.c_int]),
+    "pbl_sort_profile_read": (C.c_int, [C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "pbl_device_malloc": (C.c_int, [C.POINTER(_vp), _u64]),
     "pbl_device_free": (C.c_int, [_vp]),
     "pbl_host_malloc_pinned": (C.c_int, [C.POINTER(_vp), _u64]),

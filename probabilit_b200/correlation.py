@@ -184,21 +184,31 @@ class ImanConover(Correlator):
             pass
 
     # ------------------------------------------------------------------ the transform
-    def __call__(self, X):
+    def __call__(self, X, *, out=None):
         """Transform an input matrix X of shape (N, K); same contract as the reference's
-        ``ImanConover.__call__`` (correlation.py:368-425)."""
+        ``ImanConover.__call__`` (correlation.py:368-425).
+
+        ``out`` (extension, optional): a float64 array with X's shape and memory order to
+        receive the result (e.g. page-locked memory, so that the device-to-host copy runs at
+        PCIe speed); by default a fresh ``np.empty_like(X)`` is returned like the reference."""
         N, K = self._validate_X(X)
         if _is_cuda_tensor(X):
             return self._call_device(X, N, K)
-        return self._call_host(X, N, K)
+        return self._call_host(X, N, K, out)
 
-    def _call_host(self, X, N, K):
+    def _call_host(self, X, N, K, out=None):
         lib = _lib.require_gpu()
         device = 0 if self.device is None else int(self.device)
         Xd = X
         if Xd.dtype != np.float64 or not (Xd.flags.f_contiguous or Xd.flags.c_contiguous):
             Xd = np.asfortranarray(X, dtype=np.float64)
-        result = np.empty_like(Xd)  # correlation.py:418 (keeps the memory order of X)
+        if out is not None:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == Xd.shape
+                    and out.strides == Xd.strides):
+                raise ValueError("`out` must be a float64 array with the shape and strides of X")
+            result = out
+        else:
+            result = np.empty_like(Xd)  # correlation.py:418 (keeps the memory order of X)
         plan = self._get_plan(N, K, device)
         nbytes = Xd.nbytes
         if self._dev_bufs is None or self._dev_bufs[2] != nbytes:

@@ -28,6 +28,15 @@ const char* pbl_last_error(void) { return pbl::get_last_error(); }
 
 int64_t pbl_kernel_launches(void) { return (int64_t)pbl::g_kernel_launches.load(); }
 
+int pbl_sort_profile_enable(int on) {
+  pbl::sort_profile_enable(on != 0);
+  return kOk;
+}
+int pbl_sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys) {
+  pbl::sort_profile_read(launches, total_ms, keys);
+  return kOk;
+}
+
 int pbl_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

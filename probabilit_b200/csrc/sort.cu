@@ -1,6 +1,8 @@
 // Batched per-column onesweep LSD radix sort (see sort.cuh for the layout).
 #include "sort.cuh"
 
+#include <vector>
+
 namespace pbl {
 
 namespace {
@@ -358,6 +360,37 @@ constexpr size_t pass_smem_bytes() {
 
 }  // namespace
 
+namespace {
+struct PassEvent {
+  cudaEvent_t start, stop;
+  int64_t keys;
+};
+bool g_profile = false;
+std::vector<PassEvent> g_events;
+}  // namespace
+
+void sort_profile_enable(bool on) { g_profile = on; }
+
+void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys) {
+  int64_t nl = 0, nk = 0;
+  double ms = 0.0;
+  for (auto& e : g_events) {
+    float t = 0.f;
+    if (cudaEventSynchronize(e.stop) == cudaSuccess &&
+        cudaEventElapsedTime(&t, e.start, e.stop) == cudaSuccess) {
+      ++nl;
+      ms += t;
+      nk += e.keys;
+    }
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  g_events.clear();
+  if (launches) *launches = nl;
+  if (total_ms) *total_ms = ms;
+  if (keys) *keys = nk;
+}
+
 size_t sort_status_bytes(int ncols, uint32_t n) {
   size_t ntiles = ((size_t)n + kSortTile - 1) / kSortTile;
   return (size_t)ncols * ntiles * kRadix * sizeof(uint32_t);
@@ -404,10 +437,21 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
       tile_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.status, buf.plan, pass, ntiles);
       PBL_LAUNCH_CHECK();
     }
+    PassEvent ev{};
+    if (g_profile) {
+      cudaEventCreate(&ev.start);
+      cudaEventCreate(&ev.stop);
+      ev.keys = (int64_t)n * ncols;
+      cudaEventRecord(ev.start, stream);
+    }
     kern<<<dim3(ntiles, ncols), kSortBlock, smem, stream>>>(
         in, row_stride, col_stride, buf.keysA, buf.keysB, buf.valsA, buf.valsB, buf.hist,
         buf.status, buf.tile_counter + (size_t)pass * ncols, buf.plan, buf.error_flag, n, pass,
         ntiles, use_lookback ? 1 : 0);
+    if (g_profile) {
+      cudaEventRecord(ev.stop, stream);
+      g_events.push_back(ev);
+    }
     PBL_LAUNCH_CHECK();
   }
   return kOk;

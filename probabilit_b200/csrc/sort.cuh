@@ -56,6 +56,13 @@ constexpr int kSortTile = kSortBlock * kSortItems;
 
 size_t sort_status_bytes(int ncols, uint32_t n);
 
+// Optional CUDA-event timing of every digit-pass launch (bench.py's roofline leg): when enabled,
+// sort_columns_f64 brackets each onesweep_pass_kernel launch with events on the launching stream.
+void sort_profile_enable(bool on);
+// Drains the recorded events (synchronises them): number of pass launches, their total
+// duration in ms and the number of keys they moved.
+void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys);
+
 // Sort `ncols` columns of n doubles each; column c starts at in + c*col_stride and its rows are
 // row_stride elements apart.  On return (stream order) column c's sorted keys/rows are in
 // buffer plan[c].final_buf (1 = A, 2 = B).  error_flag[1] is set if any input is NaN.
