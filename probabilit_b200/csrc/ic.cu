@@ -66,16 +66,17 @@ __device__ __forceinline__ uint32_t block_excl_suffix_min(uint32_t v, uint32_t* 
   return excl;
 }
 
-// MODE 0: out[col][row] = ndtri(average_rank / (n+1)),  sortedX[col][pos] = value
+// For every sorted position p of a column, the value its source row must receive:
+// MODE 0: ndtri(average_rank / (n+1)), and sortedX[col][p] = the p-th smallest input
 //         (scipy.stats.rankdata 'average' + norm.ppf, correlation.py:394-395; np.sort, :423)
-// MODE 1: out[row, col] = sortedX[col][run_start + (run_len-1)/2]
+// MODE 1: sortedX[col][run_start + (run_len-1)/2]
 //         (rankdata(...).astype(int) - 1 then the gather, correlation.py:422-423)
+// The value is staged, in sorted order, in the key buffer that does NOT hold the sorted keys;
+// scatter_by_row (sort.cu) then delivers it to row vals[final][p].
 template <int MODE>
 __global__ void __launch_bounds__(kPostBlock)
-post_sort_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
-                 const uint32_t* __restrict__ valsA, const uint32_t* __restrict__ valsB,
-                 const PassPlan* __restrict__ plan, uint32_t n, double* __restrict__ sortedX,
-                 double* __restrict__ out, int64_t out_row_stride, int64_t out_col_stride) {
+post_sort_kernel(uint64_t* keysA, uint64_t* keysB, const PassPlan* __restrict__ plan, uint32_t n,
+                 double* __restrict__ sortedX) {
   __shared__ double s_val[kPostTile + 2];
   __shared__ uint32_t s_start[kPostTile];
   __shared__ uint32_t s_end[kPostTile];
@@ -86,7 +87,7 @@ post_sort_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict_
   const int tid = threadIdx.x;
   const int fb = plan[col].final_buf;
   const uint64_t* keys = (fb == 1 ? keysA : keysB) + (size_t)col * n;
-  const uint32_t* rows = (fb == 1 ? valsA : valsB) + (size_t)col * n;
+  double* stage = reinterpret_cast<double*>((fb == 1 ? keysB : keysA) + (size_t)col * n);
   double* sx = sortedX + (size_t)col * n;
   const uint32_t tile_start = blockIdx.x * (uint32_t)kPostTile;
   const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
@@ -164,7 +165,6 @@ post_sort_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict_
     __syncthreads();
   }
 
-  double* outc = out + (int64_t)col * out_col_stride;
 #pragma unroll
   for (int j = 0; j < kPostItems; ++j) {
     uint32_t p = j * kPostBlock + tid;
@@ -175,15 +175,14 @@ post_sort_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict_
         s = s_start[p];
         e = s_end[p];
       }
-      uint32_t row = ld_stream_u32(rows + g);
       if (MODE == 0) {
         double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
         double q = __ddiv_rn(avg, (double)((uint64_t)n + 1ull));
-        outc[(int64_t)row * out_row_stride] = ndtri(q);
+        stage[g] = ndtri(q);
         sx[g] = s_val[p + 1];
       } else {
         uint32_t m = s + (e - s) / 2;
-        outc[(int64_t)row * out_row_stride] = (m == g) ? sx[g] : sx[m];
+        stage[g] = sx[m];
       }
     }
   }
@@ -537,7 +536,7 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   A(&p->sort.valsB, (size_t)cb * n);
   A(&p->sort.hist, (size_t)cb * kNumPasses * kRadix);
   A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
-  A(&p->sort.tile_counter, (size_t)cb * kNumPasses);
+  A(&p->sort.tile_counter, (size_t)cb * (kNumPasses + 1));
   A(&p->sort.plan, (size_t)cb);
   A(&p->flags, 8);
   p->sort.error_flag = p->flags;
@@ -606,10 +605,11 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     PBL_RETURN_IF(sort_columns_f64(X + (int64_t)c * col_stride, row_stride, col_stride, n, nb,
                                    sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
-    post_sort_kernel<0><<<grid, kPostBlock, 0, stream>>>(
-        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, n,
-        p->sortedX + (size_t)c * n, p->scores + (size_t)c * n, 1, (int64_t)n);
+    post_sort_kernel<0><<<grid, kPostBlock, 0, stream>>>(p->sort.keysA, p->sort.keysB, p->sort.plan, n,
+                                                         p->sortedX + (size_t)c * n);
     PBL_LAUNCH_CHECK();
+    PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
+                                 p->use_lookback, stream));
   }
   return kOk;
 }
@@ -679,10 +679,11 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_RETURN_IF(sort_columns_f64(p->scores + (size_t)c * n, 1, (int64_t)n, n, nb, sort_view(p),
                                    p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
-    post_sort_kernel<1><<<grid, kPostBlock, 0, stream>>>(
-        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, n,
-        p->sortedX + (size_t)c * n, Y + (int64_t)c * col_stride, row_stride, col_stride);
+    post_sort_kernel<1><<<grid, kPostBlock, 0, stream>>>(p->sort.keysA, p->sort.keysB, p->sort.plan, n,
+                                                         p->sortedX + (size_t)c * n);
     PBL_LAUNCH_CHECK();
+    PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
+                                 col_stride, p->use_lookback, stream));
   }
   return kOk;
 }

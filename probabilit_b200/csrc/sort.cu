@@ -1,6 +1,8 @@
 // Batched per-column onesweep LSD radix sort (see sort.cuh for the layout).
 #include "sort.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace pbl {
@@ -125,13 +127,12 @@ sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint3
 // --------------------------------------------------------------------------------------
 // Fallback (debug) path without look-back: per-tile digit counts + a serial scan over tiles.
 // --------------------------------------------------------------------------------------
-template <int BLOCK, int ITEMS>
+template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 tile_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride,
                  const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
                  uint32_t* __restrict__ tile_counts, const PassPlan* __restrict__ plan,
-                 uint32_t n, int pass, int ntiles) {
-  constexpr int TILE = BLOCK * ITEMS;
+                 uint32_t n, int pass, int ntiles, int TILE) {
   __shared__ uint32_t sh[kRadix];
   const int col = blockIdx.y;
   if (!plan[col].run[pass]) return;
@@ -170,40 +171,80 @@ __global__ void tile_scan_kernel(uint32_t* __restrict__ tile_counts,
 }
 
 // --------------------------------------------------------------------------------------
-// Kernel 3: one digit pass.  Tile = BLOCK*ITEMS keys, warp-striped so that
-// (warp, item, lane) order == position order (each pass must be stable).
-//   load -> match.any ranking into warp-private histograms -> scan over warps and bins
-//   -> publish tile counts / look back for the exclusive tile prefix per bin
-//   -> scatter keys+rows into shared memory in digit order -> coalesced runs to HBM.
+// Kernel 3: one partition pass (the onesweep step).  Tile = BLOCK*ITEMS elements, warp-striped
+// so that (warp, item, lane) order == position order (every LSD pass must be stable).
+//   load -> match.any ranking, one shared-memory atomic per distinct digit and warp
+//   -> scan over warps and bins -> publish tile counts / look back for the exclusive tile
+//   prefix per bin -> scatter key+payload into shared memory in digit order -> coalesced
+//   runs out to HBM.
+// SCATTER = false: radix digit pass of the sort  (key u64 = fp64 image, payload u32 = row).
+// SCATTER = true : first half of the "scatter by row" step that follows each sort: key u32 =
+//   destination row, payload u64 = the fp64 value to deliver; digit = row >> shift, i.e. the
+//   elements are grouped into <= 256 destination windows small enough to live in L2, so that
+//   the second half (scatter_rows_kernel) writes every 128 B line of the output exactly once
+//   from L2 instead of issuing 1e8 random 8 B read-modify-writes to HBM.  Rows are a
+//   permutation, so the bin bases are known without a histogram.
 // --------------------------------------------------------------------------------------
-template <int BLOCK, int ITEMS>
-__global__ void __launch_bounds__(BLOCK, 3)
-onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride,
-                     uint64_t* __restrict__ keysA, uint64_t* __restrict__ keysB,
-                     uint32_t* __restrict__ valsA, uint32_t* __restrict__ valsB,
-                     const uint32_t* __restrict__ bin_base_all, uint32_t* __restrict__ status,
-                     uint32_t* __restrict__ tile_counter, const PassPlan* __restrict__ plan,
-                     uint32_t* __restrict__ error_flag, uint32_t n, int pass, int ntiles,
-                     int use_lookback) {
+template <bool SCATTER> struct PassTypes { using Key = uint64_t; using Val = uint32_t; };
+template <> struct PassTypes<true> { using Key = uint32_t; using Val = uint64_t; };
+
+struct PassArgs {
+  const double* raw;        // SORT: caller's column-major-or-strided doubles (src == 0)
+  int64_t row_stride, col_stride;
+  uint64_t* keysA;
+  uint64_t* keysB;
+  uint32_t* valsA;
+  uint32_t* valsB;
+  const uint32_t* bin_base_all;  // SORT: [ncols][8][256] exclusive digit histograms
+  uint32_t* status;              // [ncols][ntiles][256] look-back words (or tile offsets)
+  uint32_t* tile_counter;        // [ncols]
+  const PassPlan* plan;
+  uint32_t* error_flag;
+  uint32_t n;
+  int pass;                      // SORT: digit index;  SCATTER: unused
+  int shift;                     // SCATTER: row >> shift = window
+  int ntiles;
+  int use_lookback;
+};
+
+template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
+__global__ void __launch_bounds__(BLOCK, MINB)
+partition_pass_kernel(const PassArgs a) {
+  using Key = typename PassTypes<SCATTER>::Key;
+  using Val = typename PassTypes<SCATTER>::Val;
   constexpr int TILE = BLOCK * ITEMS;
   constexpr int NWARPS = BLOCK / 32;
   static_assert(BLOCK >= kRadix && BLOCK % 32 == 0, "one thread per bin is assumed");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);          // [TILE]
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);     // [TILE]
-  uint32_t* s_hist = s_vals + TILE;                                  // [NWARPS][kRadix]
-  uint32_t* s_goff = s_hist + NWARPS * kRadix;                       // [kRadix]
-  uint32_t* s_wsum = s_goff + kRadix;                                // [8]
-  uint32_t* s_tile = s_wsum + 8;                                     // [1]
+  uint64_t* s_big = reinterpret_cast<uint64_t*>(smem_raw);             // [TILE] 8-byte member
+  uint32_t* s_small = reinterpret_cast<uint32_t*>(s_big + TILE);       // [TILE] 4-byte member
+  uint32_t* s_hist = s_small + TILE;                                   // [NWARPS][kRadix]
+  uint32_t* s_goff = s_hist + NWARPS * kRadix;                         // [kRadix]
+  uint32_t* s_wsum = s_goff + kRadix;                                  // [8]
+  uint32_t* s_tile = s_wsum + 8;                                       // [1]
+  Key* s_keys = SCATTER ? reinterpret_cast<Key*>(s_small) : reinterpret_cast<Key*>(s_big);
+  Val* s_vals = SCATTER ? reinterpret_cast<Val*>(s_big) : reinterpret_cast<Val*>(s_small);
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
-  if (!plan[col].run[pass]) return;
-  const int src = plan[col].src[pass];
-  const int dst = (src == 1) ? 2 : 1;
-  const int shift = pass * kRadixBits;
+  const uint32_t n = a.n;
+  int src, dst, shift;
+  if (SCATTER) {
+    // sorted rows live in vals[final]; the values to deliver were staged in keys[other]
+    src = a.plan[col].final_buf;
+    dst = (src == 1) ? 2 : 1;
+    shift = a.shift;
+  } else {
+    if (!a.plan[col].run[a.pass]) return;
+    src = a.plan[col].src[a.pass];
+    dst = (src == 1) ? 2 : 1;
+    shift = a.pass * kRadixBits;
+  }
+  auto digit = [&](Key k) -> uint32_t {
+    return SCATTER ? (uint32_t)(k >> shift) : ((uint32_t)((uint64_t)k >> shift) & (kRadix - 1));
+  };
 
-  if (tid == 0) *s_tile = atomicAdd(&tile_counter[col], 1u);
+  if (tid == 0) *s_tile = atomicAdd(&a.tile_counter[col], 1u);
   for (int i = tid; i < NWARPS * kRadix; i += BLOCK) s_hist[i] = 0;
   __syncthreads();
   const uint32_t tile = *s_tile;
@@ -211,47 +252,50 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
   const uint32_t nvalid = min((uint32_t)TILE, n - tile_start);
   const uint32_t warp = tid >> 5, lane = tid & 31;
   const uint32_t pos0 = warp * (ITEMS * 32) + lane;
+  const Key kPad = SCATTER ? (Key)(((uint64_t)(kRadix - 1)) << shift) : (Key)~0ull;  // last bin
 
-  // ---- load keys (padding = all-ones: last bin, after every real key) ----
-  uint64_t key[ITEMS];
-  if (src == 0) {
-    const double* colp = raw + (int64_t)col * col_stride + (int64_t)tile_start * row_stride;
+  // ---- load keys (padding sorts after every real key of the tile) ----
+  Key key[ITEMS];
+  if (SCATTER) {
+    const uint32_t* kin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t pos = pos0 + u * 32;
-      key[u] = ~0ull;
+      key[u] = (pos < nvalid) ? (Key)ld_stream_u32(kin + pos) : kPad;
+    }
+  } else if (src == 0) {
+    const double* colp = a.raw + (int64_t)col * a.col_stride + (int64_t)tile_start * a.row_stride;
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) {
+      uint32_t pos = pos0 + u * 32;
+      key[u] = kPad;
       if (pos < nvalid) {
-        double d = ld_stream_f64(colp + (int64_t)pos * row_stride);
-        key[u] = flip_f64((uint64_t)__double_as_longlong(d));
+        double d = ld_stream_f64(colp + (int64_t)pos * a.row_stride);
+        key[u] = (Key)flip_f64((uint64_t)__double_as_longlong(d));
       }
     }
   } else {
-    const uint64_t* kin = (src == 1 ? keysA : keysB) + (size_t)col * n + tile_start;
+    const uint64_t* kin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t pos = pos0 + u * 32;
-      key[u] = (pos < nvalid) ? ld_stream_u64(kin + pos) : ~0ull;
+      key[u] = (pos < nvalid) ? (Key)ld_stream_u64(kin + pos) : kPad;
     }
   }
 
-  // ---- rank inside the warp ----
+  // ---- rank inside the warp: the ITEMS chains are independent (one ATOMS each) ----
   uint32_t rank[ITEMS];
   uint32_t* wh = s_hist + warp * kRadix;
   const uint32_t lt = lanemask_lt();
 #pragma unroll
   for (int u = 0; u < ITEMS; ++u) {
-    uint32_t bin = digit_of(key[u], shift);
+    uint32_t bin = digit(key[u]);
     uint32_t m = __match_any_sync(0xFFFFFFFFu, bin);
     uint32_t below = __popc(m & lt);
-    int leader = 31 - __clz(m);  // highest lane of the group: below + 1 == group size
     uint32_t base = 0;
-    if ((int)lane == leader) {
-      base = wh[bin];
-      wh[bin] = base + below + 1;
-    }
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if ((m >> lane) == 1u) base = atomicAdd(&wh[bin], below + 1);  // highest lane of the group
+    base = __shfl_sync(0xFFFFFFFFu, base, 31 - __clz(m));
     rank[u] = base + below;
-    __syncwarp();
   }
   __syncthreads();
 
@@ -282,8 +326,8 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
 
     // ---- exclusive prefix of this bin over all earlier tiles ----
     uint32_t excl = 0;
-    uint32_t* st = status + (size_t)col * ntiles * kRadix;
-    if (use_lookback) {
+    uint32_t* st = a.status + (size_t)col * a.ntiles * kRadix;
+    if (a.use_lookback) {
       if (tile == 0) {
         st_relaxed_u32(&st[tid], cnt | kFlagInclusive);
       } else {
@@ -294,7 +338,7 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
           uint32_t w = ld_relaxed_u32(&st[(size_t)t * kRadix + tid]);
           if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
             if (++spins > kSpinLimit) {
-              atomicExch(&error_flag[0], 1u);
+              atomicExch(&a.error_flag[0], 1u);
               break;
             }
             continue;
@@ -308,8 +352,14 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
     } else {
       excl = st[(size_t)tile * kRadix + tid];
     }
-    const uint32_t* bin_base = bin_base_all + ((size_t)col * kNumPasses + pass) * kRadix;
-    s_goff[tid] = bin_base[tid] + excl - bin_start;  // + position in tile order = global slot
+    uint32_t base;
+    if (SCATTER) {
+      uint64_t b = (uint64_t)tid << shift;  // rows are a permutation of 0..n-1
+      base = (uint32_t)(b < n ? b : n);
+    } else {
+      base = a.bin_base_all[((size_t)col * kNumPasses + a.pass) * kRadix + tid];
+    }
+    s_goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) s_hist[w * kRadix + tid] += bin_start;
   }
@@ -318,20 +368,28 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
   // ---- scatter to shared memory in digit order ----
 #pragma unroll
   for (int u = 0; u < ITEMS; ++u) {
-    uint32_t bin = digit_of(key[u], shift);
-    rank[u] += wh[bin];
+    rank[u] += wh[digit(key[u])];
     s_keys[rank[u]] = key[u];
   }
-  if (src == 0) {
+  if (!SCATTER && src == 0) {
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = tile_start + pos0 + u * 32;
+    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = (Val)(tile_start + pos0 + u * 32);
   } else {
-    const uint32_t* vin = (src == 1 ? valsA : valsB) + (size_t)col * n + tile_start;
-    uint32_t v[ITEMS];
+    Val v[ITEMS];
+    if (SCATTER) {
+      const uint64_t* vin = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) {
-      uint32_t pos = pos0 + u * 32;
-      v[u] = (pos < nvalid) ? ld_stream_u32(vin + pos) : 0u;
+      for (int u = 0; u < ITEMS; ++u) {
+        uint32_t pos = pos0 + u * 32;
+        v[u] = (pos < nvalid) ? (Val)ld_stream_u64(vin + pos) : (Val)0;
+      }
+    } else {
+      const uint32_t* vin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u) {
+        uint32_t pos = pos0 + u * 32;
+        v[u] = (pos < nvalid) ? (Val)ld_stream_u32(vin + pos) : (Val)0;
+      }
     }
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = v[u];
@@ -339,23 +397,102 @@ onesweep_pass_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t
   __syncthreads();
 
   // ---- coalesced runs out to HBM ----
-  uint64_t* kout = (dst == 1 ? keysA : keysB) + (size_t)col * n;
-  uint32_t* vout = (dst == 1 ? valsA : valsB) + (size_t)col * n;
+  // SORT: keys -> keys[dst], rows -> vals[dst].   SCATTER: rows -> vals[dst], values -> keys[src]
+  // (keys[src], the sorted keys, are dead once the post-sort kernel has consumed them).
+  uint64_t* out_big = (SCATTER ? (src == 1 ? a.keysA : a.keysB) : (dst == 1 ? a.keysA : a.keysB)) + (size_t)col * n;
+  uint32_t* out_small = (dst == 1 ? a.valsA : a.valsB) + (size_t)col * n;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     uint32_t pos = j * BLOCK + tid;
     if (pos < nvalid) {
-      uint64_t k = s_keys[pos];
-      uint32_t g = s_goff[digit_of(k, shift)] + pos;
-      kout[g] = k;
-      vout[g] = s_vals[pos];
+      Key k = s_keys[pos];
+      uint32_t g = s_goff[digit(k)] + pos;
+      if (SCATTER) {
+        out_small[g] = (uint32_t)k;
+        out_big[g] = (uint64_t)s_vals[pos];
+      } else {
+        out_big[g] = (uint64_t)k;
+        out_small[g] = (uint32_t)s_vals[pos];
+      }
     }
   }
 }
 
-template <int BLOCK, int ITEMS>
-constexpr size_t pass_smem_bytes() {
-  return (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + kRadix * 4 + 8 * 4 + 16;
+// Second half of the scatter: out[row] = value for (row, value) pairs that are already grouped by
+// destination window (see above).  Blocks walk the column in order, so the windows being written
+// at any moment total a few MB and stay in L2 until every line is complete.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
+                    const uint32_t* __restrict__ valsA, const uint32_t* __restrict__ valsB,
+                    const PassPlan* __restrict__ plan, uint32_t n, int partitioned,
+                    double* __restrict__ out, int64_t out_row_stride, int64_t out_col_stride) {
+  const int col = blockIdx.y;
+  const int fb = plan[col].final_buf;
+  const int ob = (fb == 1) ? 2 : 1;
+  // partitioned: rows in vals[other], values in keys[final];  direct: rows in vals[final], values in keys[other]
+  const uint32_t* rows = ((partitioned ? ob : fb) == 1 ? valsA : valsB) + (size_t)col * n;
+  const uint64_t* vals = ((partitioned ? fb : ob) == 1 ? keysA : keysB) + (size_t)col * n;
+  double* outc = out + (int64_t)col * out_col_stride;
+  constexpr int U = 8;
+  const uint32_t base = blockIdx.x * (256u * U) + threadIdx.x;
+  uint32_t r[U];
+  uint64_t v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint32_t i = base + u * 256u;
+    if (i < n) {
+      r[u] = ld_stream_u32(rows + i);
+      v[u] = ld_stream_u64(vals + i);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint32_t i = base + u * 256u;
+    if (i < n) outc[(int64_t)r[u] * out_row_stride] = __longlong_as_double((long long)v[u]);
+  }
+}
+
+struct SortCfg {
+  int block, items;
+};
+static SortCfg g_cfg = {0, 0};
+
+const SortCfg& sort_cfg() {
+  if (!g_cfg.block) {
+    const char* e = getenv("PBL_SORT_CFG");
+    int c = e ? atoi(e) : 0;
+    switch (c) {
+      case 1: g_cfg = {512, 8}; break;
+      case 2: g_cfg = {256, 12}; break;
+      case 3: g_cfg = {384, 12}; break;
+      case 4: g_cfg = {512, 6}; break;
+      default: g_cfg = {256, 16}; break;
+    }
+  }
+  return g_cfg;
+}
+
+template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
+int launch_pass(const PassArgs& a, int ncols, cudaStream_t stream) {
+  auto kern = partition_pass_kernel<BLOCK, ITEMS, MINB, SCATTER>;
+  constexpr size_t smem = (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + kRadix * 4 + 8 * 4 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3(a.ntiles, ncols), BLOCK, smem, stream>>>(a);
+  return kOk;
+}
+
+template <bool SCATTER>
+int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
+  const SortCfg& c = sort_cfg();
+  if (c.block == 512 && c.items == 8) return launch_pass<512, 8, 2, SCATTER>(a, ncols, stream);
+  if (c.block == 256 && c.items == 12) return launch_pass<256, 12, 4, SCATTER>(a, ncols, stream);
+  if (c.block == 384 && c.items == 12) return launch_pass<384, 12, 2, SCATTER>(a, ncols, stream);
+  if (c.block == 512 && c.items == 6) return launch_pass<512, 6, 3, SCATTER>(a, ncols, stream);
+  return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
 }
 
 }  // namespace
@@ -391,8 +528,11 @@ void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys) {
   if (keys) *keys = nk;
 }
 
+int sort_tile_size() { return sort_cfg().block * sort_cfg().items; }
+
 size_t sort_status_bytes(int ncols, uint32_t n) {
-  size_t ntiles = ((size_t)n + kSortTile - 1) / kSortTile;
+  size_t tile = (size_t)sort_tile_size();
+  size_t ntiles = ((size_t)n + tile - 1) / tile;
   return (size_t)ncols * ntiles * kRadix * sizeof(uint32_t);
 }
 
@@ -403,9 +543,10 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
     set_last_error("sort_columns_f64: n exceeds 2^30-1 rows per column");
     return kBadShape;
   }
-  const int ntiles = (int)(((size_t)n + kSortTile - 1) / kSortTile);
+  const int tile = sort_tile_size();
+  const int ntiles = (int)(((size_t)n + tile - 1) / tile);
   PBL_CUDA_CHECK(cudaMemsetAsync(buf.hist, 0, (size_t)ncols * kNumPasses * kRadix * 4, stream));
-  PBL_CUDA_CHECK(cudaMemsetAsync(buf.tile_counter, 0, (size_t)ncols * kNumPasses * 4, stream));
+  PBL_CUDA_CHECK(cudaMemsetAsync(buf.tile_counter, 0, (size_t)ncols * (kNumPasses + 1) * 4, stream));
 
   {
     constexpr int HB = 512, HU = 4;
@@ -419,24 +560,35 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
   sort_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.hist, buf.plan, n);
   PBL_LAUNCH_CHECK();
 
-  auto kern = onesweep_pass_kernel<kSortBlock, kSortItems>;
-  constexpr size_t smem = pass_smem_bytes<kSortBlock, kSortItems>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    PBL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   const size_t status_bytes = sort_status_bytes(ncols, n);
+  PassArgs a{};
+  a.raw = in;
+  a.row_stride = row_stride;
+  a.col_stride = col_stride;
+  a.keysA = buf.keysA;
+  a.keysB = buf.keysB;
+  a.valsA = buf.valsA;
+  a.valsB = buf.valsB;
+  a.bin_base_all = buf.hist;
+  a.status = buf.status;
+  a.plan = buf.plan;
+  a.error_flag = buf.error_flag;
+  a.n = n;
+  a.shift = 0;
+  a.ntiles = ntiles;
+  a.use_lookback = use_lookback ? 1 : 0;
   for (int pass = 0; pass < kNumPasses; ++pass) {
     if (use_lookback) {
       PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, status_bytes, stream));
     } else {
-      tile_hist_kernel<kSortBlock, kSortItems><<<dim3(ntiles, ncols), kSortBlock, 0, stream>>>(
-          in, row_stride, col_stride, buf.keysA, buf.keysB, buf.status, buf.plan, n, pass, ntiles);
+      tile_hist_kernel<256><<<dim3(ntiles, ncols), 256, 0, stream>>>(
+          in, row_stride, col_stride, buf.keysA, buf.keysB, buf.status, buf.plan, n, pass, ntiles, tile);
       PBL_LAUNCH_CHECK();
       tile_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.status, buf.plan, pass, ntiles);
       PBL_LAUNCH_CHECK();
     }
+    a.pass = pass;
+    a.tile_counter = buf.tile_counter + (size_t)pass * ncols;
     PassEvent ev{};
     if (g_profile) {
       cudaEventCreate(&ev.start);
@@ -444,16 +596,55 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
       ev.keys = (int64_t)n * ncols;
       cudaEventRecord(ev.start, stream);
     }
-    kern<<<dim3(ntiles, ncols), kSortBlock, smem, stream>>>(
-        in, row_stride, col_stride, buf.keysA, buf.keysB, buf.valsA, buf.valsB, buf.hist,
-        buf.status, buf.tile_counter + (size_t)pass * ncols, buf.plan, buf.error_flag, n, pass,
-        ntiles, use_lookback ? 1 : 0);
+    PBL_RETURN_IF(launch_pass_cfg<false>(a, ncols, stream));
     if (g_profile) {
       cudaEventRecord(ev.stop, stream);
       g_events.push_back(ev);
     }
     PBL_LAUNCH_CHECK();
   }
+  return kOk;
+}
+
+int scatter_shift_for(uint32_t n) {
+  // <= 256 destination windows; a single window (no partition pass) below 2^19 rows
+  int bits = 0;
+  while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+  return bits > 19 ? std::max(19, bits - 8) : 32;
+}
+
+// Deliver staged values to their rows: out[col][rows[p]] = value[p] for every sorted position p.
+// On entry (stream order) rows are in vals[final] and values in keys[other] of each column.
+int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
+                   int64_t col_stride, bool use_lookback, cudaStream_t stream) {
+  if (n == 0 || ncols <= 0) return kOk;
+  const int shift = scatter_shift_for(n);
+  const bool partitioned = shift < 32 && use_lookback && row_stride == 1;
+  if (partitioned) {
+    const int tile = sort_tile_size();
+    const int ntiles = (int)(((size_t)n + tile - 1) / tile);
+    PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, sort_status_bytes(ncols, n), stream));
+    PassArgs a{};
+    a.keysA = buf.keysA;
+    a.keysB = buf.keysB;
+    a.valsA = buf.valsA;
+    a.valsB = buf.valsB;
+    a.status = buf.status;
+    a.tile_counter = buf.tile_counter + (size_t)kNumPasses * ncols;
+    a.plan = buf.plan;
+    a.error_flag = buf.error_flag;
+    a.n = n;
+    a.shift = shift;
+    a.ntiles = ntiles;
+    a.use_lookback = 1;
+    PBL_CUDA_CHECK(cudaMemsetAsync(a.tile_counter, 0, (size_t)ncols * 4, stream));
+    PBL_RETURN_IF(launch_pass_cfg<true>(a, ncols, stream));
+    PBL_LAUNCH_CHECK();
+  }
+  dim3 grid((unsigned)(((size_t)n + 2047) / 2048), (unsigned)ncols);
+  scatter_rows_kernel<<<grid, 256, 0, stream>>>(buf.keysA, buf.keysB, buf.valsA, buf.valsB, buf.plan,
+                                               n, partitioned ? 1 : 0, out, row_stride, col_stride);
+  PBL_LAUNCH_CHECK();
   return kOk;
 }
 

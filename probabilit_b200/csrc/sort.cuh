@@ -45,15 +45,13 @@ struct SortBuffers {
   uint32_t* valsB = nullptr;
   uint32_t* hist = nullptr;      // [ncols][8][256]
   uint32_t* status = nullptr;    // [ncols][ntiles][256]
-  uint32_t* tile_counter = nullptr;  // [8 passes][ncols]
+  uint32_t* tile_counter = nullptr;  // [8 passes + 1 scatter pass][ncols]
   PassPlan* plan = nullptr;      // [ncols]
   uint32_t* error_flag = nullptr;    // [4]: watchdog / NaN flags
 };
 
-constexpr int kSortBlock = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortBlock * kSortItems;
-
+// tile size of the partition kernel in use (PBL_SORT_CFG selects the instantiation)
+int sort_tile_size();
 size_t sort_status_bytes(int ncols, uint32_t n);
 
 // Optional CUDA-event timing of every digit-pass launch (bench.py's roofline leg): when enabled,
@@ -68,5 +66,12 @@ void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys);
 // buffer plan[c].final_buf (1 = A, 2 = B).  error_flag[1] is set if any input is NaN.
 int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, uint32_t n,
                      int ncols, const SortBuffers& buf, bool use_lookback, cudaStream_t stream);
+
+// "Scatter by row" that follows each sort: out[col][rows[p] * row_stride] = value[p], where
+// rows[] is the sorted payload (vals[final]) and value[] was staged by the caller in keys[other].
+// For long columns it runs as a partition pass into <= 256 L2-sized row windows followed by a
+// window-local scatter (see sort.cu); short columns are scattered directly.
+int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
+                   int64_t col_stride, bool use_lookback, cudaStream_t stream);
 
 }  // namespace pbl

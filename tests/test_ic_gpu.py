@@ -47,7 +47,8 @@ def test_stages_against_oracle(ic_golden, name):
 
 
 @pytest.mark.parametrize("lookback", ["1", "0"])
-@pytest.mark.parametrize("n,k,seed", [(100_000, 5, 0), (300_001, 3, 1), (4097, 7, 2), (65_536, 16, 3)])
+@pytest.mark.parametrize("n,k,seed", [(100_000, 5, 0), (300_001, 3, 1), (4097, 7, 2), (65_536, 16, 3),
+                                      (700_001, 3, 4)])
 def test_random_problems_bit_exact(monkeypatch, n, k, seed, lookback):
     """Multi-tile sorts (look-back across tiles) with and without the look-back path."""
     from probabilit_b200 import ImanConover
@@ -72,6 +73,23 @@ def test_heavy_ties_multi_tile():
     X[:, 1] = rng.integers(0, 3, n)
     X[:, 2] = np.round(rng.normal(size=n), 2)
     X[:, 3] = rng.normal(size=n)
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got = ImanConover().set_target(C)(X)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_heavy_ties_partitioned_scatter():
+    """n > 2^19 rows: the scatter runs as window partition + window-local scatter; discrete data
+    makes every tile take the tie-run path and skips most digit passes."""
+    from probabilit_b200 import ImanConover
+
+    rng = np.random.default_rng(8)
+    n, k = 1_200_000, 3
+    X = np.empty((n, k), order="F")
+    X[:, 0] = rng.poisson(3.0, n)
+    X[:, 1] = rng.normal(size=n)
+    X[:, 2] = rng.binomial(10, 0.4, n)
     C = random_target(rng, k)
     want = oic.iman_conover(X, C)
     got = ImanConover().set_target(C)(X)
