@@ -219,8 +219,9 @@ partition_pass_kernel(const PassArgs a) {
   uint64_t* s_big = reinterpret_cast<uint64_t*>(smem_raw);             // [TILE] 8-byte member
   uint32_t* s_small = reinterpret_cast<uint32_t*>(s_big + TILE);       // [TILE] 4-byte member
   uint32_t* s_hist = s_small + TILE;                                   // [NWARPS][kRadix]
-  uint32_t* s_goff = s_hist + NWARPS * kRadix;                         // [kRadix]
-  uint32_t* s_wsum = s_goff + kRadix;                                  // [8]
+  uint32_t* s_goff = s_hist + NWARPS * kRadix;                         // [kRadix] global slot - tile position
+  uint32_t* s_bstart = s_goff + kRadix;                                // [kRadix] tile-local bin start
+  uint32_t* s_wsum = s_bstart + kRadix;                                // [8]
   uint32_t* s_tile = s_wsum + 8;                                       // [1]
   Key* s_keys = SCATTER ? reinterpret_cast<Key*>(s_small) : reinterpret_cast<Key*>(s_big);
   Val* s_vals = SCATTER ? reinterpret_cast<Val*>(s_big) : reinterpret_cast<Val*>(s_small);
@@ -283,32 +284,25 @@ partition_pass_kernel(const PassArgs a) {
     }
   }
 
-  // ---- rank inside the warp: the ITEMS chains are independent (one ATOMS each) ----
-  uint32_t rank[ITEMS];
+  // ---- early counts: warp-private digit histograms (fire-and-forget shared atomics) ----
   uint32_t* wh = s_hist + warp * kRadix;
-  const uint32_t lt = lanemask_lt();
 #pragma unroll
-  for (int u = 0; u < ITEMS; ++u) {
-    uint32_t bin = digit(key[u]);
-    uint32_t m = __match_any_sync(0xFFFFFFFFu, bin);
-    uint32_t below = __popc(m & lt);
-    uint32_t base = 0;
-    if ((m >> lane) == 1u) base = atomicAdd(&wh[bin], below + 1);  // highest lane of the group
-    base = __shfl_sync(0xFFFFFFFFu, base, 31 - __clz(m));
-    rank[u] = base + below;
-  }
+  for (int u = 0; u < ITEMS; ++u) atomicAdd(&wh[digit(key[u])], 1u);
   __syncthreads();
 
-  // ---- per bin: exclusive scan over warps, tile total, exclusive scan over bins ----
+  // ---- per bin: exclusive scan over warps, tile total; publish it for the tiles behind us as
+  //      early as possible, then exclusive scan over bins ----
   uint32_t cnt = 0, bin_start = 0;
+  uint32_t* st = a.status + (size_t)col * a.ntiles * kRadix;
   if (tid < kRadix) {
+    uint32_t wc[NWARPS];
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-      uint32_t c = s_hist[w * kRadix + tid];
-      s_hist[w * kRadix + tid] = cnt;
-      cnt += c;
-    }
+    for (int w = 0; w < NWARPS; ++w) wc[w] = s_hist[w * kRadix + tid];
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) cnt += wc[w];
     if (tid == kRadix - 1) cnt -= (uint32_t)TILE - nvalid;  // drop the padding keys
+    if (a.use_lookback)
+      st_relaxed_u32(&st[(size_t)tile * kRadix + tid], cnt | (tile == 0 ? kFlagInclusive : kFlagPartial));
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -317,21 +311,87 @@ partition_pass_kernel(const PassArgs a) {
     }
     if (lane == 31) s_wsum[warp] = incl;
     bin_start = incl - cnt;
+    // warp-private counters become running offsets *within the bin* (the bin start is added
+    // below, once the scan over bins is complete)
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      s_hist[w * kRadix + tid] = run;
+      run += wc[w];
+    }
   }
   __syncthreads();
   if (tid < kRadix) {
 #pragma unroll
     for (int w = 0; w < kRadix / 32; ++w)
       if ((uint32_t)w < warp) bin_start += s_wsum[w];
+    s_bstart[tid] = bin_start;
+  }
 
-    // ---- exclusive prefix of this bin over all earlier tiles ----
-    uint32_t excl = 0;
-    uint32_t* st = a.status + (size_t)col * a.ntiles * kRadix;
+  // ---- rank inside the warp.  Three phases so that the ITEMS match / atomic / shuffle chains
+  //      overlap instead of serialising: (1) all MATCH.ANY, (2) one predicated shared-memory
+  //      atomic per digit group, issued by its highest lane, (3) broadcast + lane offset. ----
+  uint32_t rank[ITEMS];
+  {
+    const uint32_t lt = lanemask_lt();
+    uint32_t m[ITEMS];
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) m[u] = __match_any_sync(0xFFFFFFFFu, digit(key[u]));
+    const uint32_t wh_addr = (uint32_t)__cvta_generic_to_shared(wh);
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) {
+      uint32_t leader = ((m[u] >> lane) == 1u) ? 1u : 0u;  // highest lane of its group
+      uint32_t add = __popc(m[u]);
+      uint32_t addr = wh_addr + digit(key[u]) * 4u;
+      uint32_t base = 0;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+          : "+r"(base)
+          : "r"(addr), "r"(add), "r"(leader)
+          : "memory");
+      rank[u] = base;
+    }
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u)
+      rank[u] = __shfl_sync(0xFFFFFFFFu, rank[u], 31 - __clz(m[u])) + __popc(m[u] & lt);
+  }
+  __syncthreads();  // bin starts visible to everyone
+
+  // ---- scatter to shared memory in digit order ----
+#pragma unroll
+  for (int u = 0; u < ITEMS; ++u) {
+    rank[u] += s_bstart[digit(key[u])];
+    s_keys[rank[u]] = key[u];
+  }
+  if (!SCATTER && src == 0) {
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = (Val)(tile_start + pos0 + u * 32);
+  } else {
+    Val v[ITEMS];
+    if (SCATTER) {
+      const uint64_t* vin = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u) {
+        uint32_t pos = pos0 + u * 32;
+        v[u] = (pos < nvalid) ? (Val)ld_stream_u64(vin + pos) : (Val)0;
+      }
+    } else {
+      const uint32_t* vin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u) {
+        uint32_t pos = pos0 + u * 32;
+        v[u] = (pos < nvalid) ? (Val)ld_stream_u32(vin + pos) : (Val)0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = v[u];
+  }
+
+  // ---- exclusive prefix of this bin over all earlier tiles (they published long ago) ----
+  uint32_t excl = 0;
+  if (tid < kRadix) {
     if (a.use_lookback) {
-      if (tile == 0) {
-        st_relaxed_u32(&st[tid], cnt | kFlagInclusive);
-      } else {
-        st_relaxed_u32(&st[(size_t)tile * kRadix + tid], cnt | kFlagPartial);
+      if (tile != 0) {
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
         while (true) {
@@ -360,40 +420,8 @@ partition_pass_kernel(const PassArgs a) {
       base = a.bin_base_all[((size_t)col * kNumPasses + a.pass) * kRadix + tid];
     }
     s_goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) s_hist[w * kRadix + tid] += bin_start;
   }
-  __syncthreads();
 
-  // ---- scatter to shared memory in digit order ----
-#pragma unroll
-  for (int u = 0; u < ITEMS; ++u) {
-    rank[u] += wh[digit(key[u])];
-    s_keys[rank[u]] = key[u];
-  }
-  if (!SCATTER && src == 0) {
-#pragma unroll
-    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = (Val)(tile_start + pos0 + u * 32);
-  } else {
-    Val v[ITEMS];
-    if (SCATTER) {
-      const uint64_t* vin = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
-#pragma unroll
-      for (int u = 0; u < ITEMS; ++u) {
-        uint32_t pos = pos0 + u * 32;
-        v[u] = (pos < nvalid) ? (Val)ld_stream_u64(vin + pos) : (Val)0;
-      }
-    } else {
-      const uint32_t* vin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
-#pragma unroll
-      for (int u = 0; u < ITEMS; ++u) {
-        uint32_t pos = pos0 + u * 32;
-        v[u] = (pos < nvalid) ? (Val)ld_stream_u32(vin + pos) : (Val)0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = v[u];
-  }
   __syncthreads();
 
   // ---- coalesced runs out to HBM ----
@@ -454,6 +482,7 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
 
 struct SortCfg {
   int block, items;
+  int minb = 0;
 };
 static SortCfg g_cfg = {0, 0};
 
@@ -466,6 +495,8 @@ const SortCfg& sort_cfg() {
       case 2: g_cfg = {256, 12}; break;
       case 3: g_cfg = {384, 12}; break;
       case 4: g_cfg = {512, 6}; break;
+      case 5: g_cfg = {256, 8}; break;
+      case 6: g_cfg = {256, 16, }; g_cfg.minb = 3; break;
       default: g_cfg = {256, 16}; break;
     }
   }
@@ -475,7 +506,7 @@ const SortCfg& sort_cfg() {
 template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
 int launch_pass(const PassArgs& a, int ncols, cudaStream_t stream) {
   auto kern = partition_pass_kernel<BLOCK, ITEMS, MINB, SCATTER>;
-  constexpr size_t smem = (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + kRadix * 4 + 8 * 4 + 16;
+  constexpr size_t smem = (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + 2 * kRadix * 4 + 8 * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     PBL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -489,10 +520,12 @@ template <bool SCATTER>
 int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
   const SortCfg& c = sort_cfg();
   if (c.block == 512 && c.items == 8) return launch_pass<512, 8, 2, SCATTER>(a, ncols, stream);
-  if (c.block == 256 && c.items == 12) return launch_pass<256, 12, 4, SCATTER>(a, ncols, stream);
+  if (c.block == 256 && c.items == 12) return launch_pass<256, 12, 3, SCATTER>(a, ncols, stream);
   if (c.block == 384 && c.items == 12) return launch_pass<384, 12, 2, SCATTER>(a, ncols, stream);
   if (c.block == 512 && c.items == 6) return launch_pass<512, 6, 3, SCATTER>(a, ncols, stream);
-  return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
+  if (c.block == 256 && c.items == 8) return launch_pass<256, 8, 5, SCATTER>(a, ncols, stream);
+  if (c.minb == 3) return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
+  return launch_pass<256, 16, 2, SCATTER>(a, ncols, stream);
 }
 
 }  // namespace
