@@ -286,8 +286,13 @@ partition_pass_kernel(const PassArgs a) {
 
   // ---- early counts: warp-private digit histograms (fire-and-forget shared atomics) ----
   uint32_t* wh = s_hist + warp * kRadix;
+  const uint32_t wh_addr = (uint32_t)__cvta_generic_to_shared(wh);
 #pragma unroll
-  for (int u = 0; u < ITEMS; ++u) atomicAdd(&wh[digit(key[u])], 1u);
+  for (int u = 0; u < ITEMS; ++u) {
+    // plain per-lane reduction: nvcc would otherwise warp-aggregate it with MATCH.ANY, whose
+    // cost grows with the number of distinct digits in the warp (the ADU pipe saturates)
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(wh_addr + digit(key[u]) * 4u), "r"(1u) : "memory");
+  }
   __syncthreads();
 
   // ---- per bin: exclusive scan over warps, tile total; publish it for the tiles behind us as
@@ -328,16 +333,27 @@ partition_pass_kernel(const PassArgs a) {
     s_bstart[tid] = bin_start;
   }
 
-  // ---- rank inside the warp.  Three phases so that the ITEMS match / atomic / shuffle chains
-  //      overlap instead of serialising: (1) all MATCH.ANY, (2) one predicated shared-memory
-  //      atomic per digit group, issued by its highest lane, (3) broadcast + lane offset. ----
+  // ---- rank inside the warp.  Three phases so that the ITEMS chains overlap instead of
+  //      serialising: (1) the mask of lanes holding the same digit, built from 8 ballots (one
+  //      per digit bit; MATCH.ANY is avoided on purpose, see above), (2) one predicated
+  //      shared-memory atomic per digit group, issued by its highest lane, (3) broadcast + lane
+  //      offset. ----
   uint32_t rank[ITEMS];
   {
     const uint32_t lt = lanemask_lt();
     uint32_t m[ITEMS];
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) m[u] = __match_any_sync(0xFFFFFFFFu, digit(key[u]));
-    const uint32_t wh_addr = (uint32_t)__cvta_generic_to_shared(wh);
+    for (int u = 0; u < ITEMS; ++u) {
+      const uint32_t d = digit(key[u]);
+      uint32_t mm = 0xFFFFFFFFu;
+#pragma unroll
+      for (int b = 0; b < kRadixBits; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+        mm &= bit ? bal : ~bal;
+      }
+      m[u] = mm;
+    }
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t leader = ((m[u] >> lane) == 1u) ? 1u : 0u;  // highest lane of its group
