@@ -29,7 +29,10 @@ typedef enum pbl_status {
   PBL_NON_FINITE = 2,            /* ValueError "array must not contain infs or NaNs" (scipy check_finite at :409) */
   PBL_BAD_SHAPE = 3,             /* ValueError from Correlator._validate_X, correlation.py:181-202 */
   PBL_CUDA_ERROR = 4,
-  PBL_INTERNAL = 5
+  PBL_INTERNAL = 5,
+  PBL_RETRY = 6 /* stage API only (pbl_ic_stage_status): the data are too dense for the 40-bit sort window;
+                   the plan has switched to the exact 64-bit sort, repeat from pbl_ic_stage_begin.
+                   pbl_ic_plan_run / pbl_iman_conover_f64 handle this internally. */
 } pbl_status;
 
 /* ---- library ---- */

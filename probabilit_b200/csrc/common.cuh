@@ -16,6 +16,7 @@ enum Status : int {
   kBadShape = 3,
   kCudaError = 4,
   kInternal = 5,             // look-back watchdog fired, etc.
+  kRetry = 6,                // stage API only: repeat from stage_begin (the plan now sorts on 64 bits)
 };
 
 void set_last_error(const std::string& msg);

@@ -31,6 +31,9 @@ namespace {
 constexpr int kPostBlock = 256;
 constexpr int kPostItems = 8;
 constexpr int kPostTile = kPostBlock * kPostItems;
+constexpr int kHalo = 64;                      // window values may repeat in runs of < kHalo keys
+constexpr int kWin = kPostTile + 2 * kHalo;
+constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 64;
 
 __device__ __forceinline__ uint32_t block_excl_prefix_max(uint32_t v, uint32_t* s_w) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,38 +69,112 @@ __device__ __forceinline__ uint32_t block_excl_suffix_min(uint32_t v, uint32_t* 
   return excl;
 }
 
-// For every sorted position p of a column, the value its source row must receive:
-// MODE 0: ndtri(average_rank / (n+1)), and sortedX[col][p] = the p-th smallest input
-//         (scipy.stats.rankdata 'average' + norm.ppf, correlation.py:394-395; np.sort, :423)
-// MODE 1: sortedX[col][run_start + (run_len-1)/2]
-//         (rankdata(...).astype(int) - 1 then the gather, correlation.py:422-423)
-// The value is staged, in sorted order, in the key buffer that does NOT hold the sorted keys;
-// scatter_by_row (sort.cu) then delivers it to row vals[final][p].
+// Consumes one column that the windowed sort left ordered by window value (sort.cuh):
+//  (1) completes the order inside every run of equal window values (runs of < kHalo keys are
+//      re-ordered by their full 64-bit keys in shared memory; a longer run of *distinct* keys
+//      raises kFlagWindowRetry and the caller repeats the sort on all 64 bits);
+//  (2) finds the tie runs (equal values) and, for every sorted position p, the value its source
+//      row must receive:
+//      MODE 0: ndtri(average_rank / (n+1)), and sortedX[col][p] = the p-th smallest input
+//              (scipy.stats.rankdata 'average' + norm.ppf, correlation.py:394-395; np.sort, :423)
+//      MODE 1: sortedX[col][run_start + (run_len-1)/2]
+//              (rankdata(...).astype(int) - 1 then the gather, correlation.py:422-423)
+//  (3) stages value and row, in sorted order, in the "other" ping-pong buffer (the one that does
+//      not hold the sorted keys); scatter_by_row (sort.cu) then delivers value -> row.
 template <int MODE>
 __global__ void __launch_bounds__(kPostBlock)
-post_sort_kernel(uint64_t* keysA, uint64_t* keysB, const PassPlan* __restrict__ plan, uint32_t n,
-                 double* __restrict__ sortedX) {
-  __shared__ double s_val[kPostTile + 2];
-  __shared__ uint32_t s_start[kPostTile];
-  __shared__ uint32_t s_end[kPostTile];
-  __shared__ uint32_t s_w[kPostBlock / 32];
-  __shared__ uint32_t s_lo, s_hi;
+post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB,
+                 const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
+                 int window_bits, uint32_t n, double* __restrict__ sortedX,
+                 uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  uint64_t* s_raw = reinterpret_cast<uint64_t*>(psm);        // [kWin] keys as the sort left them
+  uint64_t* s_key = s_raw + kWin;                            // [kWin] completed order
+  uint32_t* s_rawv = reinterpret_cast<uint32_t*>(s_key + kWin);  // [kWin] rows as sorted
+  uint32_t* s_row = s_rawv + kWin;                           // [kWin] rows, completed order
+  uint32_t* s_start = s_row + kWin;                          // [kPostTile]
+  uint32_t* s_end = s_start + kPostTile;                     // [kPostTile]
+  uint32_t* s_w = s_end + kPostTile;                         // [8]
+  uint32_t* s_lohi = s_w + 8;                                // [2]
+  double* s_val = reinterpret_cast<double*>(s_raw);          // [kPostTile + 2], reuses s_raw
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
   const int fb = plan[col].final_buf;
   const uint64_t* keys = (fb == 1 ? keysA : keysB) + (size_t)col * n;
+  const uint32_t* rows_in = (fb == 1 ? valsA : valsB) + (size_t)col * n;
   double* stage = reinterpret_cast<double*>((fb == 1 ? keysB : keysA) + (size_t)col * n);
+  uint32_t* rows_out = (fb == 1 ? valsB : valsA) + (size_t)col * n;
   double* sx = sortedX + (size_t)col * n;
+  const KeyMap map = load_key_map(kminmax, col, window_bits);
   const uint32_t tile_start = blockIdx.x * (uint32_t)kPostTile;
   const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
+  const int64_t wbase = (int64_t)tile_start - kHalo;  // global index of window slot 0
+
+  for (int i = tid; i < kWin; i += kPostBlock) {
+    int64_t g = wbase + i;
+    uint64_t k = 0;
+    uint32_t r = 0;
+    if (g >= 0 && g < (int64_t)n) {
+      k = ld_stream_u64(keys + g);
+      r = ld_stream_u32(rows_in + g);
+    }
+    s_raw[i] = k;
+    s_rawv[i] = r;
+  }
+  __syncthreads();
+
+  // ---- (1) complete the order inside runs of equal window values ----
+  int retry = 0;
+  for (int i = tid; i < kWin; i += kPostBlock) {
+    const int64_t g = wbase + i;
+    if (g < 0 || g >= (int64_t)n) continue;
+    const uint64_t my = s_raw[i];
+    const uint64_t mw = window_value(my, map);
+    uint32_t cnt = 0;
+    int L = 0, R = 0;
+    bool diff = false, open = false;
+    for (int j = i - 1;; --j) {
+      if (j < 0) { open = (wbase + j >= 0); break; }          // unseen element left of the window
+      if (wbase + j < 0) break;                               // start of the column
+      const uint64_t kj = s_raw[j];
+      if (window_value(kj, map) != mw) break;
+      if (L == kHalo) { open = true; break; }
+      cnt += (kj <= my) ? 1u : 0u;                            // equal keys keep their order
+      diff |= (kj != my);
+      ++L;
+    }
+    for (int j = i + 1;; ++j) {
+      if (j >= kWin) { open |= (wbase + j < (int64_t)n); break; }
+      if (wbase + j >= (int64_t)n) break;                     // end of the column
+      const uint64_t kj = s_raw[j];
+      if (window_value(kj, map) != mw) break;
+      if (R == kHalo) { open = true; break; }
+      cnt += (kj < my) ? 1u : 0u;
+      diff |= (kj != my);
+      ++R;
+    }
+    if (L + R + 1 > kHalo - 1) open = true;  // every member of the run must reach the same verdict
+    int dst = i;
+    if (diff) {
+      if (!open) {
+        dst = i - L + (int)cnt;
+      } else if (i + R >= kHalo - 1 && i - L <= kHalo + (int)nvalid) {
+        retry = 1;  // cannot be completed here and it matters for this tile's output
+      }
+    }
+    s_key[dst] = my;
+    s_row[dst] = s_rawv[i];
+  }
+  if (retry) flags[kFlagWindowRetry] = 1u;
+  __syncthreads();
 
   // values with a one-element halo on both sides; NaN outside the column (never ties)
-  for (uint32_t i = tid; i < nvalid + 2; i += kPostBlock) {
-    int64_t g = (int64_t)tile_start + i - 1;
+  for (uint32_t q = tid; q < nvalid + 2; q += kPostBlock) {
+    int64_t g = (int64_t)tile_start + q - 1;
     double v = __longlong_as_double(0x7FF8000000000000LL);
-    if (g >= 0 && g < (int64_t)n) v = key_to_double(ld_stream_u64(keys + g));
-    s_val[i] = v;
+    if (g >= 0 && g < (int64_t)n) v = key_to_double(s_key[kHalo - 1 + q]);
+    s_val[q] = v;
   }
   __syncthreads();
   int tie = 0;
@@ -127,29 +204,30 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, const PassPlan* __restrict__ 
       en[i] = run;
     }
     uint32_t suf = block_excl_suffix_min(run, s_w);
-    // runs that cross the tile boundary: binary search in the sorted column
+    // tie runs that cross the tile boundary: binary search on the window value in the column
+    // (valid because such a run is pure: any impure long run has raised kFlagWindowRetry)
     if (tid == 0) {
       uint32_t lo = tile_start, hi = tile_start + nvalid - 1;
       if (s_val[0] == s_val[1]) {
-        double v = s_val[1];
-        uint32_t a = 0, b = tile_start;  // first q in [0, tile_start) with val[q] >= v
+        const uint64_t w = window_value(s_key[kHalo], map);
+        uint32_t a = 0, b = tile_start;  // first q in [0, tile_start) with window(q) >= w
         while (a < b) {
           uint32_t mid = a + (b - a) / 2;
-          if (key_to_double(keys[mid]) < v) a = mid + 1; else b = mid;
+          if (window_value(keys[mid], map) < w) a = mid + 1; else b = mid;
         }
         lo = a;
       }
       if (s_val[nvalid] == s_val[nvalid + 1]) {
-        double v = s_val[nvalid];
-        uint32_t a = tile_start + nvalid, b = n;  // first q with val[q] > v
+        const uint64_t w = window_value(s_key[kHalo + nvalid - 1], map);
+        uint32_t a = tile_start + nvalid, b = n;  // first q with window(q) > w
         while (a < b) {
           uint32_t mid = a + (b - a) / 2;
-          if (key_to_double(keys[mid]) > v) b = mid; else a = mid + 1;
+          if (window_value(keys[mid], map) > w) b = mid; else a = mid + 1;
         }
         hi = a - 1;
       }
-      s_lo = lo;
-      s_hi = hi;
+      s_lohi[0] = lo;
+      s_lohi[1] = hi;
     }
     __syncthreads();
 #pragma unroll
@@ -158,8 +236,8 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, const PassPlan* __restrict__ 
       if (p < nvalid) {
         uint32_t s = max(st[i], pre);
         uint32_t e = min(en[i], suf);
-        s_start[p] = (s == 0) ? s_lo : s - 1;
-        s_end[p] = (e == 0xFFFFFFFFu) ? s_hi : e;
+        s_start[p] = (s == 0) ? s_lohi[0] : s - 1;
+        s_end[p] = (e == 0xFFFFFFFFu) ? s_lohi[1] : e;
       }
     }
     __syncthreads();
@@ -175,11 +253,13 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, const PassPlan* __restrict__ 
         s = s_start[p];
         e = s_end[p];
       }
+      const uint32_t row = s_row[kHalo + p];
+      rows_out[g] = row & kRowMask;
       if (MODE == 0) {
         double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
         double q = __ddiv_rn(avg, (double)((uint64_t)n + 1ull));
         stage[g] = ndtri(q);
-        sx[g] = s_val[p + 1];
+        sx[g] = (row & kNegZeroFlag) ? -0.0 : s_val[p + 1];
       } else {
         uint32_t m = s + (e - s) / 2;
         stage[g] = sx[m];
@@ -362,7 +442,7 @@ chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsu
   for (int j = 0; j < k; ++j) {
     double d = W[(size_t)j * k + j];
     if (!(d > 0.0)) {  // same acceptance as LAPACK dpotrf: pivot must be > 0 and not NaN
-      if (tid == 0) flags[2] = 1u;
+      if (tid == 0) flags[kFlagNotPD] = 1u;
       // keep the rest of the pipeline well defined (its output is discarded by the caller)
       for (int e = tid; e < k * k; e += nth) T[e] = 0.0;
       return;
@@ -512,6 +592,8 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   PBL_CUDA_CHECK(cudaGetDevice(&p->device));
   const char* lb = getenv("PBL_SORT_LOOKBACK");
   p->use_lookback = !(lb && lb[0] == '0');
+  const char* wb = getenv("PBL_WINDOW_BITS");
+  p->window_bits = (wb && atoi(wb) == 64) ? 64 : 40;
 
   // column batch: as many columns per launch as fit in ~45% of free memory
   size_t free_b = 0, total_b = 0;
@@ -534,9 +616,10 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   A(&p->sort.keysB, (size_t)cb * n);
   A(&p->sort.valsA, (size_t)cb * n);
   A(&p->sort.valsB, (size_t)cb * n);
-  A(&p->sort.hist, (size_t)cb * kNumPasses * kRadix);
+  A(&p->sort.hist, (size_t)cb * kMaxPasses * kRadix);
   A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
-  A(&p->sort.tile_counter, (size_t)cb * (kNumPasses + 1));
+  A(&p->sort.tile_counter, (size_t)cb * (kMaxPasses + 1));
+  A(&p->sort.kminmax, (size_t)cb * 2);
   A(&p->sort.plan, (size_t)cb);
   A(&p->flags, 8);
   p->sort.error_flag = p->flags;
@@ -574,6 +657,7 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->sort.status);
   cudaFree(p->sort.tile_counter);
   cudaFree(p->sort.plan);
+  cudaFree(p->sort.kminmax);
   cudaFree(p->flags);
   cudaFree(p->sortedX);
   cudaFree(p->scores);
@@ -597,16 +681,28 @@ int ic_plan_set_target(IcPlan* p, const double* P_lower_host) {
 // ======================================================================================
 static SortBuffers sort_view(const IcPlan* p) { return p->sort; }
 
+static int post_sort_attr() {
+  static bool done = false;
+  if (!done) {
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(post_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(post_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
+    done = true;
+  }
+  return kOk;
+}
+
 int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream) {
   const uint32_t n = (uint32_t)p->n;
   for (int c = col0; c < col0 + ncols; c += p->col_batch) {
     int nb = std::min(p->col_batch, col0 + ncols - c);
     PBL_RETURN_IF(sort_columns_f64(X + (int64_t)c * col_stride, row_stride, col_stride, n, nb,
-                                   sort_view(p), p->use_lookback, stream));
+                                   p->window_bits, sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
-    post_sort_kernel<0><<<grid, kPostBlock, 0, stream>>>(p->sort.keysA, p->sort.keysB, p->sort.plan, n,
-                                                         p->sortedX + (size_t)c * n);
+    PBL_RETURN_IF(post_sort_attr());
+    post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
+        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->flags);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
                                  p->use_lookback, stream));
@@ -676,11 +772,13 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
   const uint32_t n = (uint32_t)p->n;
   for (int c = col0; c < col0 + ncols; c += p->col_batch) {
     int nb = std::min(p->col_batch, col0 + ncols - c);
-    PBL_RETURN_IF(sort_columns_f64(p->scores + (size_t)c * n, 1, (int64_t)n, n, nb, sort_view(p),
-                                   p->use_lookback, stream));
+    PBL_RETURN_IF(sort_columns_f64(p->scores + (size_t)c * n, 1, (int64_t)n, n, nb, p->window_bits,
+                                   sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
-    post_sort_kernel<1><<<grid, kPostBlock, 0, stream>>>(p->sort.keysA, p->sort.keysB, p->sort.plan, n,
-                                                         p->sortedX + (size_t)c * n);
+    PBL_RETURN_IF(post_sort_attr());
+    post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
+        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->flags);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
                                  col_stride, p->use_lookback, stream));
@@ -692,15 +790,21 @@ int ic_read_status(IcPlan* p, cudaStream_t stream) {
   uint32_t h[8];
   PBL_CUDA_CHECK(cudaMemcpyAsync(h, p->flags, sizeof(h), cudaMemcpyDeviceToHost, stream));
   PBL_CUDA_CHECK(cudaStreamSynchronize(stream));
-  if (h[0]) {
+  if (h[kFlagWatchdog]) {
     set_last_error("radix sort look-back watchdog fired (internal error)");
     return kInternal;
   }
-  if (h[1]) {
+  if (h[kFlagNaN]) {
     set_last_error("array must not contain infs or NaNs");
     return kNonFinite;
   }
-  if (h[2]) {
+  if (h[kFlagWindowRetry] && p->window_bits < 64) {
+    // the data are too dense for the 40-bit window: from now on this plan sorts on all 64 bits
+    p->window_bits = 64;
+    set_last_error("windowed sort could not be completed; repeat the call (full 64-bit sort)");
+    return kRetry;
+  }
+  if (h[kFlagNotPD]) {
     set_last_error("Rank data correlation not positive definite.");
     return kNotPositiveDefinite;
   }
@@ -709,13 +813,18 @@ int ic_read_status(IcPlan* p, cudaStream_t stream) {
 
 int ic_plan_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, double* Y, int64_t yrs,
                 int64_t ycs, cudaStream_t stream) {
-  PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
-  PBL_RETURN_IF(ic_stage_rank_scores(p, X, xrs, xcs, 0, p->k, stream));
-  PBL_RETURN_IF(ic_stage_gram(p, stream));
-  PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
-  PBL_RETURN_IF(ic_stage_transform(p, stream));
-  PBL_RETURN_IF(ic_stage_rank_gather(p, Y, yrs, ycs, 0, p->k, stream));
-  return ic_read_status(p, stream);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
+    PBL_RETURN_IF(ic_stage_rank_scores(p, X, xrs, xcs, 0, p->k, stream));
+    PBL_RETURN_IF(ic_stage_gram(p, stream));
+    PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
+    PBL_RETURN_IF(ic_stage_transform(p, stream));
+    PBL_RETURN_IF(ic_stage_rank_gather(p, Y, yrs, ycs, 0, p->k, stream));
+    int st = ic_read_status(p, stream);
+    if (st != kRetry) return st;
+  }
+  set_last_error("windowed sort retry did not converge (internal error)");
+  return kInternal;
 }
 
 }  // namespace pbl

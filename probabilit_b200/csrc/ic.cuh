@@ -12,6 +12,7 @@ struct IcPlan {
   int k = 0;           // columns (variables)
   int col_batch = 0;   // columns sorted per launch batch (bounds the sort workspace)
   bool use_lookback = true;
+  int window_bits = 40;  // sort window (sort.cuh); switches to 64 after a kRetry status
   bool has_target = false;
 
   SortBuffers sort;            // sized for col_batch columns
@@ -25,7 +26,7 @@ struct IcPlan {
   double* work = nullptr;      // [k][k] scratch: R, then Q (lower Cholesky factor)
   double* T = nullptr;         // [k][k] row-major, upper triangular: correlated = scores @ T
   double* P = nullptr;         // [k][k] row-major lower Cholesky factor of the target C
-  uint32_t* flags = nullptr;   // [8]: 0 look-back watchdog, 1 NaN in X, 2 not PD, 3 non-finite scores
+  uint32_t* flags = nullptr;   // [8], see SortFlag in sort.cuh
   size_t bytes = 0;            // device bytes held by the plan
 };
 

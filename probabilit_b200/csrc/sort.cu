@@ -1,4 +1,4 @@
-// Batched per-column onesweep LSD radix sort (see sort.cuh for the layout).
+// Batched per-column windowed onesweep LSD radix sort + scatter-by-row (see sort.cuh).
 #include "sort.cuh"
 
 #include <algorithm>
@@ -11,62 +11,125 @@ namespace {
 
 constexpr uint32_t kSpinLimit = 1u << 24;  // look-back watchdog: fail loudly instead of hanging
 
-__device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift) {
-  return (uint32_t)(key >> shift) & (kRadix - 1);
+// fp64 -> sort key (order-preserving, -0.0 folded onto +0.0); *neg_zero tells the caller
+__device__ __forceinline__ uint64_t key_of_double(double d, bool* neg_zero) {
+  uint64_t bits = (uint64_t)__double_as_longlong(d);
+  const bool nz = bits == 0x8000000000000000ull;
+  if (nz) bits = 0;
+  *neg_zero = nz;
+  return flip_f64(bits);
 }
 
 // --------------------------------------------------------------------------------------
-// Kernel 1: all 8 digit histograms of every column in one read of the input (8 B / key),
-// plus the NaN check the reference gets from scipy's check_finite (correlation.py:409).
-// Shared-memory atomics; the two most significant digits (sign/exponent bits: few distinct
-// values for real data, i.e. same-address conflicts) are warp-aggregated with match.any.
+// Kernel 0: per-column min / max key (for the window map) and the NaN check the reference
+// gets from scipy's check_finite (correlation.py:409).  8 B / key, pure streaming.
 // --------------------------------------------------------------------------------------
+__global__ void minmax_init_kernel(uint64_t* __restrict__ kminmax, int ncols) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) {
+    kminmax[2 * c] = ~0ull;
+    kminmax[2 * c + 1] = 0ull;
+  }
+}
+
 template <int BLOCK, int UNROLL>
 __global__ void __launch_bounds__(BLOCK)
-sort_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride,
-                 uint32_t n, uint32_t* __restrict__ hist, uint32_t* __restrict__ error_flag) {
-  __shared__ uint32_t sh[kNumPasses][kRadix];
-  for (int i = threadIdx.x; i < kNumPasses * kRadix; i += BLOCK) (&sh[0][0])[i] = 0;
-  __syncthreads();
+col_minmax_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride, uint32_t n,
+                  uint64_t* __restrict__ kminmax, uint32_t* __restrict__ error_flag) {
+  __shared__ uint64_t s_lo[BLOCK / 32], s_hi[BLOCK / 32];
   const int col = blockIdx.y;
   const double* colp = raw + (int64_t)col * col_stride;
-  const uint32_t lane = lane_id();
+  uint64_t lo = ~0ull, hi = 0ull;
   bool saw_nan = false;
+  const uint64_t step = (uint64_t)gridDim.x * BLOCK * UNROLL;
+  for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n; base += step) {
+    double d[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      uint64_t i = base + (uint64_t)u * BLOCK + threadIdx.x;
+      d[u] = (i < n) ? ld_stream_f64(colp + (int64_t)i * row_stride) : colp[0];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      bool nz;
+      uint64_t k = key_of_double(d[u], &nz);
+      saw_nan |= (d[u] != d[u]);
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BLOCK / 32; ++w) {
+      lo = min(lo, s_lo[w]);
+      hi = max(hi, s_hi[w]);
+    }
+    atomicMin((unsigned long long*)&kminmax[2 * col], (unsigned long long)lo);
+    atomicMax((unsigned long long*)&kminmax[2 * col + 1], (unsigned long long)hi);
+  }
+  if (saw_nan) error_flag[kFlagNaN] = 1u;
+}
+
+// --------------------------------------------------------------------------------------
+// Kernel 1: the digit histograms of every column's window values in one read of the input
+// (8 B / key).  Shared-memory atomics; the two most significant digits (few distinct values for
+// real data, i.e. same-address conflicts) are warp-aggregated with match.any, which is cheap
+// exactly when few distinct values are present.
+// --------------------------------------------------------------------------------------
+template <int BLOCK, int UNROLL, int NP>
+__global__ void __launch_bounds__(BLOCK)
+sort_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride, uint32_t n,
+                 uint32_t* __restrict__ hist, const uint64_t* __restrict__ kminmax, int window_bits) {
+  __shared__ uint32_t sh[NP][kRadix];
+  for (int i = threadIdx.x; i < NP * kRadix; i += BLOCK) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const int col = blockIdx.y;
+  const KeyMap map = load_key_map(kminmax, col, window_bits);
+  const double* colp = raw + (int64_t)col * col_stride;
+  const uint32_t lane = lane_id();
   const uint64_t step = (uint64_t)gridDim.x * BLOCK * UNROLL;
   // the loop bound is warp-uniform so that match.any sees the full warp
   for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n; base += step) {
-    uint64_t k[UNROLL];
+    uint64_t w[UNROLL];
     bool valid[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       uint64_t i = base + (uint64_t)u * BLOCK + threadIdx.x;
       valid[u] = i < n;
       double d = valid[u] ? ld_stream_f64(colp + (int64_t)i * row_stride) : 0.0;
-      saw_nan |= (d != d);
-      k[u] = flip_f64((uint64_t)__double_as_longlong(d));
+      bool nz;
+      w[u] = window_value(key_of_double(d, &nz), map);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       if (valid[u]) {
 #pragma unroll
-        for (int p = 0; p < kNumPasses - 2; ++p) atomicAdd(&sh[p][digit_of(k[u], 8 * p)], 1u);
+        for (int p = 0; p < NP - 2; ++p) atomicAdd(&sh[p][(uint32_t)(w[u] >> (8 * p)) & 255u], 1u);
       }
-      uint32_t top = valid[u] ? (uint32_t)(k[u] >> 48) : 0xFFFFFFFFu;
+      uint32_t top = valid[u] ? (uint32_t)(w[u] >> (8 * (NP - 2))) & 0xFFFFu : 0xFFFFFFFFu;
       uint32_t m = __match_any_sync(0xFFFFFFFFu, top);
       if (valid[u] && lane == (uint32_t)(__ffs(m) - 1)) {
         uint32_t c = __popc(m);
-        atomicAdd(&sh[kNumPasses - 2][top & 255u], c);
-        atomicAdd(&sh[kNumPasses - 1][top >> 8], c);
+        atomicAdd(&sh[NP - 2][top & 255u], c);
+        atomicAdd(&sh[NP - 1][top >> 8], c);
       }
     }
   }
   __syncthreads();
-  uint32_t* h = hist + (size_t)col * kNumPasses * kRadix;
-  for (int i = threadIdx.x; i < kNumPasses * kRadix; i += BLOCK) {
+  uint32_t* h = hist + (size_t)col * kMaxPasses * kRadix;
+  for (int i = threadIdx.x; i < NP * kRadix; i += BLOCK) {
     uint32_t v = (&sh[0][0])[i];
     if (v) atomicAdd(&h[i], v);
   }
-  if (saw_nan) error_flag[1] = 1u;
 }
 
 // block-wide exclusive scan over kRadix values held one per thread (blockDim.x == kRadix)
@@ -93,14 +156,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 // passes are no-ops, which buffer each pass reads).  One block of 256 threads per column.
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRadix)
-sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint32_t n) {
+sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint32_t n, int npasses) {
   __shared__ uint32_t s_wsum[kRadix / 32];
-  __shared__ int s_const[kNumPasses];
+  __shared__ int s_const[kMaxPasses];
   const int col = blockIdx.x;
-  if (threadIdx.x < kNumPasses) s_const[threadIdx.x] = 0;
+  if (threadIdx.x < kMaxPasses) s_const[threadIdx.x] = 0;
   __syncthreads();
-  for (int p = 0; p < kNumPasses; ++p) {
-    uint32_t* h = hist + ((size_t)col * kNumPasses + p) * kRadix;
+  for (int p = 0; p < npasses; ++p) {
+    uint32_t* h = hist + ((size_t)col * kMaxPasses + p) * kRadix;
     uint32_t c = h[threadIdx.x];
     if (c == n) s_const[p] = 1;
     uint32_t e = block_excl_scan_256(c, s_wsum);
@@ -110,10 +173,10 @@ sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint3
   if (threadIdx.x == 0) {
     PassPlan pp;
     int cur = 0;
-    for (int p = 0; p < kNumPasses; ++p) {
-      bool run = !s_const[p];
+    for (int p = 0; p < kMaxPasses; ++p) {
+      bool run = p < npasses && !s_const[p];
       // the data must leave the caller's array at least once: force the last pass if needed
-      if (p == kNumPasses - 1 && cur == 0) run = true;
+      if (p == npasses - 1 && cur == 0) run = true;
       pp.run[p] = run ? 1 : 0;
       pp.src[p] = (uint8_t)cur;
       if (run) cur = (cur == 1) ? 2 : 1;
@@ -132,11 +195,13 @@ __global__ void __launch_bounds__(BLOCK)
 tile_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride,
                  const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
                  uint32_t* __restrict__ tile_counts, const PassPlan* __restrict__ plan,
-                 uint32_t n, int pass, int ntiles, int TILE) {
+                 const uint64_t* __restrict__ kminmax, int window_bits, uint32_t n, int pass,
+                 int ntiles, int TILE) {
   __shared__ uint32_t sh[kRadix];
   const int col = blockIdx.y;
   if (!plan[col].run[pass]) return;
   const int src = plan[col].src[pass];
+  const KeyMap map = load_key_map(kminmax, col, window_bits);
   for (int i = threadIdx.x; i < kRadix; i += BLOCK) sh[i] = 0;
   __syncthreads();
   const uint32_t tile = blockIdx.x;
@@ -145,12 +210,12 @@ tile_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col
   for (uint32_t pos = threadIdx.x; pos < nvalid; pos += BLOCK) {
     uint64_t k;
     if (src == 0) {
-      double d = raw[(int64_t)col * col_stride + (int64_t)(start + pos) * row_stride];
-      k = flip_f64((uint64_t)__double_as_longlong(d));
+      bool nz;
+      k = key_of_double(raw[(int64_t)col * col_stride + (int64_t)(start + pos) * row_stride], &nz);
     } else {
       k = (src == 1 ? keysA : keysB)[(size_t)col * n + start + pos];
     }
-    atomicAdd(&sh[digit_of(k, 8 * pass)], 1u);
+    atomicAdd(&sh[(uint32_t)(window_value(k, map) >> (8 * pass)) & 255u], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kRadix; i += BLOCK)
@@ -173,10 +238,10 @@ __global__ void tile_scan_kernel(uint32_t* __restrict__ tile_counts,
 // --------------------------------------------------------------------------------------
 // Kernel 3: one partition pass (the onesweep step).  Tile = BLOCK*ITEMS elements, warp-striped
 // so that (warp, item, lane) order == position order (every LSD pass must be stable).
-//   load -> match.any ranking, one shared-memory atomic per distinct digit and warp
-//   -> scan over warps and bins -> publish tile counts / look back for the exclusive tile
-//   prefix per bin -> scatter key+payload into shared memory in digit order -> coalesced
-//   runs out to HBM.
+//   load -> early per-warp digit counts -> tile counts published for the tiles behind us
+//   -> ballot-based ranking, one shared-memory atomic per distinct digit and warp
+//   -> scatter key+payload into shared memory in digit order -> look back for the exclusive
+//   tile prefix per bin -> coalesced runs out to HBM.
 // SCATTER = false: radix digit pass of the sort  (key u64 = fp64 image, payload u32 = row).
 // SCATTER = true : first half of the "scatter by row" step that follows each sort: key u32 =
 //   destination row, payload u64 = the fp64 value to deliver; digit = row >> shift, i.e. the
@@ -199,10 +264,12 @@ struct PassArgs {
   uint32_t* status;              // [ncols][ntiles][256] look-back words (or tile offsets)
   uint32_t* tile_counter;        // [ncols]
   const PassPlan* plan;
+  const uint64_t* kminmax;       // SORT: [ncols][2]
   uint32_t* error_flag;
   uint32_t n;
   int pass;                      // SORT: digit index;  SCATTER: unused
   int shift;                     // SCATTER: row >> shift = window
+  int window_bits;               // SORT
   int ntiles;
   int use_lookback;
 };
@@ -229,20 +296,26 @@ partition_pass_kernel(const PassArgs a) {
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
   const uint32_t n = a.n;
-  int src, dst, shift;
+  // SORT:    reads (keys, rows)[src] (or the raw column), writes (keys, rows)[dst]
+  // SCATTER: reads rows + staged values from buffer "other", writes rows + values to "final"
+  int src, dst;
+  uint32_t tsh;
+  uint64_t kmin = 0;
   if (SCATTER) {
-    // sorted rows live in vals[final]; the values to deliver were staged in keys[other]
-    src = a.plan[col].final_buf;
-    dst = (src == 1) ? 2 : 1;
-    shift = a.shift;
+    dst = a.plan[col].final_buf;
+    src = (dst == 1) ? 2 : 1;
+    tsh = (uint32_t)a.shift;
   } else {
     if (!a.plan[col].run[a.pass]) return;
     src = a.plan[col].src[a.pass];
     dst = (src == 1) ? 2 : 1;
-    shift = a.pass * kRadixBits;
+    const KeyMap map = load_key_map(a.kminmax, col, a.window_bits);
+    kmin = map.kmin;
+    tsh = map.sh + (uint32_t)a.pass * kRadixBits;
   }
   auto digit = [&](Key k) -> uint32_t {
-    return SCATTER ? (uint32_t)(k >> shift) : ((uint32_t)((uint64_t)k >> shift) & (kRadix - 1));
+    return SCATTER ? (uint32_t)((uint32_t)k >> tsh)
+                   : ((uint32_t)(((uint64_t)k - kmin) >> tsh) & (uint32_t)(kRadix - 1));
   };
 
   if (tid == 0) *s_tile = atomicAdd(&a.tile_counter[col], 1u);
@@ -253,26 +326,28 @@ partition_pass_kernel(const PassArgs a) {
   const uint32_t nvalid = min((uint32_t)TILE, n - tile_start);
   const uint32_t warp = tid >> 5, lane = tid & 31;
   const uint32_t pos0 = warp * (ITEMS * 32) + lane;
-  const Key kPad = SCATTER ? (Key)(((uint64_t)(kRadix - 1)) << shift) : (Key)~0ull;  // last bin
 
-  // ---- load keys (padding sorts after every real key of the tile) ----
+  // ---- load keys; padding (positions >= nvalid) is forced into the last bin, where it sorts
+  //      after every real key of the tile because it also has the highest positions ----
   Key key[ITEMS];
+  uint32_t negzero = 0;  // SORT from raw: bit u set if item u was -0.0
   if (SCATTER) {
     const uint32_t* kin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t pos = pos0 + u * 32;
-      key[u] = (pos < nvalid) ? (Key)ld_stream_u32(kin + pos) : kPad;
+      key[u] = (pos < nvalid) ? (Key)ld_stream_u32(kin + pos) : (Key)0;
     }
   } else if (src == 0) {
     const double* colp = a.raw + (int64_t)col * a.col_stride + (int64_t)tile_start * a.row_stride;
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t pos = pos0 + u * 32;
-      key[u] = kPad;
+      key[u] = (Key)0;
       if (pos < nvalid) {
-        double d = ld_stream_f64(colp + (int64_t)pos * a.row_stride);
-        key[u] = (Key)flip_f64((uint64_t)__double_as_longlong(d));
+        bool nz;
+        key[u] = (Key)key_of_double(ld_stream_f64(colp + (int64_t)pos * a.row_stride), &nz);
+        negzero |= (nz ? 1u : 0u) << u;
       }
     }
   } else {
@@ -280,9 +355,12 @@ partition_pass_kernel(const PassArgs a) {
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t pos = pos0 + u * 32;
-      key[u] = (pos < nvalid) ? (Key)ld_stream_u64(kin + pos) : kPad;
+      key[u] = (pos < nvalid) ? (Key)ld_stream_u64(kin + pos) : (Key)0;
     }
   }
+  uint32_t dig[ITEMS];  // 8-bit digits, packed 4 per register by the compiler's choice
+#pragma unroll
+  for (int u = 0; u < ITEMS; ++u) dig[u] = (pos0 + u * 32 < nvalid) ? digit(key[u]) : (uint32_t)(kRadix - 1);
 
   // ---- early counts: warp-private digit histograms (fire-and-forget shared atomics) ----
   uint32_t* wh = s_hist + warp * kRadix;
@@ -291,7 +369,7 @@ partition_pass_kernel(const PassArgs a) {
   for (int u = 0; u < ITEMS; ++u) {
     // plain per-lane reduction: nvcc would otherwise warp-aggregate it with MATCH.ANY, whose
     // cost grows with the number of distinct digits in the warp (the ADU pipe saturates)
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(wh_addr + digit(key[u]) * 4u), "r"(1u) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(wh_addr + dig[u] * 4u), "r"(1u) : "memory");
   }
   __syncthreads();
 
@@ -344,7 +422,7 @@ partition_pass_kernel(const PassArgs a) {
     uint32_t m[ITEMS];
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
-      const uint32_t d = digit(key[u]);
+      const uint32_t d = dig[u];
       uint32_t mm = 0xFFFFFFFFu;
 #pragma unroll
       for (int b = 0; b < kRadixBits; ++b) {
@@ -358,7 +436,7 @@ partition_pass_kernel(const PassArgs a) {
     for (int u = 0; u < ITEMS; ++u) {
       uint32_t leader = ((m[u] >> lane) == 1u) ? 1u : 0u;  // highest lane of its group
       uint32_t add = __popc(m[u]);
-      uint32_t addr = wh_addr + digit(key[u]) * 4u;
+      uint32_t addr = wh_addr + dig[u] * 4u;
       uint32_t base = 0;
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
@@ -376,16 +454,17 @@ partition_pass_kernel(const PassArgs a) {
   // ---- scatter to shared memory in digit order ----
 #pragma unroll
   for (int u = 0; u < ITEMS; ++u) {
-    rank[u] += s_bstart[digit(key[u])];
+    rank[u] += s_bstart[dig[u]];
     s_keys[rank[u]] = key[u];
   }
   if (!SCATTER && src == 0) {
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = (Val)(tile_start + pos0 + u * 32);
+    for (int u = 0; u < ITEMS; ++u)
+      s_vals[rank[u]] = (Val)((tile_start + pos0 + u * 32) | (((negzero >> u) & 1u) ? kNegZeroFlag : 0u));
   } else {
     Val v[ITEMS];
     if (SCATTER) {
-      const uint64_t* vin = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
+      const uint64_t* vin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
 #pragma unroll
       for (int u = 0; u < ITEMS; ++u) {
         uint32_t pos = pos0 + u * 32;
@@ -404,8 +483,8 @@ partition_pass_kernel(const PassArgs a) {
   }
 
   // ---- exclusive prefix of this bin over all earlier tiles (they published long ago) ----
-  uint32_t excl = 0;
   if (tid < kRadix) {
+    uint32_t excl = 0;
     if (a.use_lookback) {
       if (tile != 0) {
         int64_t t = (int64_t)tile - 1;
@@ -414,7 +493,7 @@ partition_pass_kernel(const PassArgs a) {
           uint32_t w = ld_relaxed_u32(&st[(size_t)t * kRadix + tid]);
           if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
             if (++spins > kSpinLimit) {
-              atomicExch(&a.error_flag[0], 1u);
+              atomicExch(&a.error_flag[kFlagWatchdog], 1u);
               break;
             }
             continue;
@@ -430,20 +509,17 @@ partition_pass_kernel(const PassArgs a) {
     }
     uint32_t base;
     if (SCATTER) {
-      uint64_t b = (uint64_t)tid << shift;  // rows are a permutation of 0..n-1
+      uint64_t b = (uint64_t)tid << tsh;  // rows are a permutation of 0..n-1
       base = (uint32_t)(b < n ? b : n);
     } else {
-      base = a.bin_base_all[((size_t)col * kNumPasses + a.pass) * kRadix + tid];
+      base = a.bin_base_all[((size_t)col * kMaxPasses + a.pass) * kRadix + tid];
     }
     s_goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
   }
-
   __syncthreads();
 
   // ---- coalesced runs out to HBM ----
-  // SORT: keys -> keys[dst], rows -> vals[dst].   SCATTER: rows -> vals[dst], values -> keys[src]
-  // (keys[src], the sorted keys, are dead once the post-sort kernel has consumed them).
-  uint64_t* out_big = (SCATTER ? (src == 1 ? a.keysA : a.keysB) : (dst == 1 ? a.keysA : a.keysB)) + (size_t)col * n;
+  uint64_t* out_big = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n;
   uint32_t* out_small = (dst == 1 ? a.valsA : a.valsB) + (size_t)col * n;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
@@ -473,9 +549,10 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
   const int col = blockIdx.y;
   const int fb = plan[col].final_buf;
   const int ob = (fb == 1) ? 2 : 1;
-  // partitioned: rows in vals[other], values in keys[final];  direct: rows in vals[final], values in keys[other]
-  const uint32_t* rows = ((partitioned ? ob : fb) == 1 ? valsA : valsB) + (size_t)col * n;
-  const uint64_t* vals = ((partitioned ? fb : ob) == 1 ? keysA : keysB) + (size_t)col * n;
+  // partitioned: (rows, values) in buffer "final";  direct: still in buffer "other"
+  const int b = partitioned ? fb : ob;
+  const uint32_t* rows = (b == 1 ? valsA : valsB) + (size_t)col * n;
+  const uint64_t* vals = (b == 1 ? keysA : keysB) + (size_t)col * n;
   double* outc = out + (int64_t)col * out_col_stride;
   constexpr int U = 8;
   const uint32_t base = blockIdx.x * (256u * U) + threadIdx.x;
@@ -505,15 +582,14 @@ static SortCfg g_cfg = {0, 0};
 const SortCfg& sort_cfg() {
   if (!g_cfg.block) {
     const char* e = getenv("PBL_SORT_CFG");
-    int c = e ? atoi(e) : 0;
+    int c = e ? atoi(e) : 6;
     switch (c) {
       case 1: g_cfg = {512, 8}; break;
       case 2: g_cfg = {256, 12}; break;
       case 3: g_cfg = {384, 12}; break;
-      case 4: g_cfg = {512, 6}; break;
       case 5: g_cfg = {256, 8}; break;
-      case 6: g_cfg = {256, 16, }; g_cfg.minb = 3; break;
-      default: g_cfg = {256, 16}; break;
+      case 0: g_cfg = {256, 16}; g_cfg.minb = 2; break;
+      default: g_cfg = {256, 16}; g_cfg.minb = 3; break;
     }
   }
   return g_cfg;
@@ -538,21 +614,18 @@ int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
   if (c.block == 512 && c.items == 8) return launch_pass<512, 8, 2, SCATTER>(a, ncols, stream);
   if (c.block == 256 && c.items == 12) return launch_pass<256, 12, 3, SCATTER>(a, ncols, stream);
   if (c.block == 384 && c.items == 12) return launch_pass<384, 12, 2, SCATTER>(a, ncols, stream);
-  if (c.block == 512 && c.items == 6) return launch_pass<512, 6, 3, SCATTER>(a, ncols, stream);
   if (c.block == 256 && c.items == 8) return launch_pass<256, 8, 5, SCATTER>(a, ncols, stream);
-  if (c.minb == 3) return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
-  return launch_pass<256, 16, 2, SCATTER>(a, ncols, stream);
+  if (c.minb == 2) return launch_pass<256, 16, 2, SCATTER>(a, ncols, stream);
+  return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
 }
 
-}  // namespace
-
-namespace {
 struct PassEvent {
   cudaEvent_t start, stop;
   int64_t keys;
 };
 bool g_profile = false;
 std::vector<PassEvent> g_events;
+
 }  // namespace
 
 void sort_profile_enable(bool on) { g_profile = on; }
@@ -586,27 +659,49 @@ size_t sort_status_bytes(int ncols, uint32_t n) {
 }
 
 int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, uint32_t n,
-                     int ncols, const SortBuffers& buf, bool use_lookback, cudaStream_t stream) {
+                     int ncols, int window_bits, const SortBuffers& buf, bool use_lookback,
+                     cudaStream_t stream) {
   if (n == 0 || ncols <= 0) return kOk;
   if (n > kMaxSortN) {
     set_last_error("sort_columns_f64: n exceeds 2^30-1 rows per column");
     return kBadShape;
   }
+  if (window_bits != 40 && window_bits != 64) {
+    set_last_error("sort_columns_f64: window_bits must be 40 or 64");
+    return kBadShape;
+  }
+  const int npasses = window_bits / kRadixBits;
   const int tile = sort_tile_size();
   const int ntiles = (int)(((size_t)n + tile - 1) / tile);
-  PBL_CUDA_CHECK(cudaMemsetAsync(buf.hist, 0, (size_t)ncols * kNumPasses * kRadix * 4, stream));
-  PBL_CUDA_CHECK(cudaMemsetAsync(buf.tile_counter, 0, (size_t)ncols * (kNumPasses + 1) * 4, stream));
+  PBL_CUDA_CHECK(cudaMemsetAsync(buf.hist, 0, (size_t)ncols * kMaxPasses * kRadix * 4, stream));
+  PBL_CUDA_CHECK(cudaMemsetAsync(buf.tile_counter, 0, (size_t)ncols * (kMaxPasses + 1) * 4, stream));
 
+  const int sms = num_sms();
+  {
+    constexpr int MB = 512, MU = 8;
+    int per_col = (int)(((size_t)n + MB * MU - 1) / (MB * MU));
+    int want = (sms * 4 + ncols - 1) / ncols;
+    dim3 grid((unsigned)std::max(1, std::min(per_col, want)), (unsigned)ncols);
+    minmax_init_kernel<<<(ncols + 255) / 256, 256, 0, stream>>>(buf.kminmax, ncols);
+    PBL_LAUNCH_CHECK();
+    col_minmax_kernel<MB, MU><<<grid, MB, 0, stream>>>(in, row_stride, col_stride, n, buf.kminmax,
+                                                      buf.error_flag);
+    PBL_LAUNCH_CHECK();
+  }
   {
     constexpr int HB = 512, HU = 4;
     int per_col = (int)(((size_t)n + HB * HU - 1) / (HB * HU));
-    int want = (num_sms() * 4 + ncols - 1) / ncols;  // ~4 resident blocks per SM over the batch
-    dim3 grid((unsigned)max(1, min(per_col, want)), (unsigned)ncols);
-    sort_hist_kernel<HB, HU><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,
-                                                     buf.error_flag);
+    int want = (sms * 4 + ncols - 1) / ncols;  // ~4 resident blocks per SM over the batch
+    dim3 grid((unsigned)std::max(1, std::min(per_col, want)), (unsigned)ncols);
+    if (npasses == 5)
+      sort_hist_kernel<HB, HU, 5><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,
+                                                          buf.kminmax, window_bits);
+    else
+      sort_hist_kernel<HB, HU, 8><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,
+                                                          buf.kminmax, window_bits);
     PBL_LAUNCH_CHECK();
   }
-  sort_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.hist, buf.plan, n);
+  sort_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.hist, buf.plan, n, npasses);
   PBL_LAUNCH_CHECK();
 
   const size_t status_bytes = sort_status_bytes(ncols, n);
@@ -621,17 +716,20 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
   a.bin_base_all = buf.hist;
   a.status = buf.status;
   a.plan = buf.plan;
+  a.kminmax = buf.kminmax;
   a.error_flag = buf.error_flag;
   a.n = n;
   a.shift = 0;
+  a.window_bits = window_bits;
   a.ntiles = ntiles;
   a.use_lookback = use_lookback ? 1 : 0;
-  for (int pass = 0; pass < kNumPasses; ++pass) {
+  for (int pass = 0; pass < npasses; ++pass) {
     if (use_lookback) {
       PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, status_bytes, stream));
     } else {
       tile_hist_kernel<256><<<dim3(ntiles, ncols), 256, 0, stream>>>(
-          in, row_stride, col_stride, buf.keysA, buf.keysB, buf.status, buf.plan, n, pass, ntiles, tile);
+          in, row_stride, col_stride, buf.keysA, buf.keysB, buf.status, buf.plan, buf.kminmax,
+          window_bits, n, pass, ntiles, tile);
       PBL_LAUNCH_CHECK();
       tile_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.status, buf.plan, pass, ntiles);
       PBL_LAUNCH_CHECK();
@@ -655,15 +753,13 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
   return kOk;
 }
 
-int scatter_shift_for(uint32_t n) {
+static int scatter_shift_for(uint32_t n) {
   // <= 256 destination windows; a single window (no partition pass) below 2^19 rows
   int bits = 0;
   while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
   return bits > 19 ? std::max(19, bits - 8) : 32;
 }
 
-// Deliver staged values to their rows: out[col][rows[p]] = value[p] for every sorted position p.
-// On entry (stream order) rows are in vals[final] and values in keys[other] of each column.
 int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
                    int64_t col_stride, bool use_lookback, cudaStream_t stream) {
   if (n == 0 || ncols <= 0) return kOk;
@@ -679,7 +775,7 @@ int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, i
     a.valsA = buf.valsA;
     a.valsB = buf.valsB;
     a.status = buf.status;
-    a.tile_counter = buf.tile_counter + (size_t)kNumPasses * ncols;
+    a.tile_counter = buf.tile_counter + (size_t)kMaxPasses * ncols;
     a.plan = buf.plan;
     a.error_flag = buf.error_flag;
     a.n = n;

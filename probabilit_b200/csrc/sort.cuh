@@ -5,13 +5,25 @@
 // src/probabilit/correlation.py:394 and :422) and np.sort (:423).
 //
 // Layout in HBM (all SoA, one contiguous run per column):
-//   keys  [ncols][n]  u64   order-preserving image of the fp64 values (common.cuh::flip_f64)
-//   vals  [ncols][n]  u32   source row of each key
+//   keys  [ncols][n]  u64   order-preserving image of the fp64 values (common.cuh::flip_f64),
+//                           -0.0 stored as +0.0 (they tie in the reference; the sign travels in
+//                           bit 31 of the payload and is restored when the sorted column is read)
+//   vals  [ncols][n]  u32   source row of each key (bits 0..29), bit 31 = "was -0.0"
 //   hist  [ncols][8][256] u32   digit histograms -> exclusive bin bases
 //   status[ncols][ntiles][256] u32   look-back words: bit31 inclusive, bit30 partial, 30-bit count
+//   kminmax[ncols][2] u64   smallest / largest key of the column
 // Columns are independent: blockIdx.y is the column, so one launch per digit pass covers the
 // whole batch.  The first pass reads the caller's doubles in place (any row stride) and
 // synthesises the payload (row index), so X is never copied or converted up front.
+//
+// WINDOWED SORT.  The passes do not sort on all 64 key bits: they sort on the `window_bits`
+// (40 by default -> 5 passes instead of 8) most significant bits of (key - kmin), i.e. on a
+// monotone image of the key.  Keys that collide in the window end up adjacent but possibly out
+// of order; the consumer (post_sort_kernel in ic.cu) completes the order inside each run of
+// equal window values, which are short for any data whose distinct values are not packed more
+// densely than 2^-40 of the column's range.  If a run of distinct keys is too long to complete
+// there, a flag is raised and the caller repeats the sort with window_bits = 64 (plain, exact
+// 8-pass LSD sort).  Results are identical either way.
 //
 // Digit passes in which every key of a column has the same digit are skipped on the device
 // (no host round trip): the scan kernel records, per column and pass, which ping-pong buffer
@@ -23,31 +35,66 @@ namespace pbl {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kNumPasses = 64 / kRadixBits;
+constexpr int kMaxPasses = 64 / kRadixBits;
 
 constexpr uint32_t kFlagInclusive = 0x80000000u;
 constexpr uint32_t kFlagPartial = 0x40000000u;
 constexpr uint32_t kValueMask = 0x3FFFFFFFu;
 constexpr uint32_t kMaxSortN = 0x3FFFFFFFu;  // 30-bit counts in the look-back words
+constexpr uint32_t kRowMask = 0x3FFFFFFFu;   // payload bits that hold the row
+constexpr uint32_t kNegZeroFlag = 0x80000000u;
+
+// error_flag[] slots shared by the sort and its consumers
+enum SortFlag : int {
+  kFlagWatchdog = 0,    // look-back spin limit hit
+  kFlagNaN = 1,         // NaN in the input column
+  kFlagNotPD = 2,       // (Iman-Conover) rank correlation not positive definite
+  kFlagReserved = 3,
+  kFlagWindowRetry = 4  // a run of distinct keys inside one window value was too long
+};
 
 // Per (column, pass) routing decided on the device by sort_scan_kernel.
 struct PassPlan {
-  uint8_t run[kNumPasses];  // 1: the pass moves data, 0: skipped (constant digit)
-  uint8_t src[kNumPasses];  // 0: raw input column, 1: buffer A, 2: buffer B
-  uint8_t final_buf;        // buffer holding the sorted column after the last pass (0/1/2)
+  uint8_t run[kMaxPasses];  // 1: the pass moves data, 0: skipped (constant digit)
+  uint8_t src[kMaxPasses];  // 0: raw input column, 1: buffer A, 2: buffer B
+  uint8_t final_buf;        // buffer holding the sorted column after the last pass (1/2)
   uint8_t pad[7];
 };
+
+// Monotone map key -> window value:  (key - kmin) >> sh  fits in window_bits bits.
+struct KeyMap {
+  uint64_t kmin;
+  uint32_t sh;
+};
+__device__ __forceinline__ KeyMap load_key_map(const uint64_t* __restrict__ kminmax, int col,
+                                               int window_bits) {
+  KeyMap m;
+  m.kmin = 0;
+  m.sh = 0;
+  if (window_bits < 64) {
+    const uint64_t lo = kminmax[2 * col], hi = kminmax[2 * col + 1];
+    const uint64_t range = hi >= lo ? hi - lo : 0;
+    const int bits = 64 - __clzll((long long)range);
+    m.kmin = lo;
+    m.sh = bits > window_bits ? (uint32_t)(bits - window_bits) : 0u;
+  }
+  return m;
+}
+__device__ __forceinline__ uint64_t window_value(uint64_t key, const KeyMap& m) {
+  return (key - m.kmin) >> m.sh;
+}
 
 struct SortBuffers {
   uint64_t* keysA = nullptr;
   uint64_t* keysB = nullptr;
   uint32_t* valsA = nullptr;
   uint32_t* valsB = nullptr;
-  uint32_t* hist = nullptr;      // [ncols][8][256]
-  uint32_t* status = nullptr;    // [ncols][ntiles][256]
+  uint32_t* hist = nullptr;          // [ncols][8][256]
+  uint32_t* status = nullptr;        // [ncols][ntiles][256]
   uint32_t* tile_counter = nullptr;  // [8 passes + 1 scatter pass][ncols]
-  PassPlan* plan = nullptr;      // [ncols]
-  uint32_t* error_flag = nullptr;    // [4]: watchdog / NaN flags
+  PassPlan* plan = nullptr;          // [ncols]
+  uint64_t* kminmax = nullptr;       // [ncols][2]
+  uint32_t* error_flag = nullptr;    // [8], see SortFlag
 };
 
 // tile size of the partition kernel in use (PBL_SORT_CFG selects the instantiation)
@@ -55,22 +102,24 @@ int sort_tile_size();
 size_t sort_status_bytes(int ncols, uint32_t n);
 
 // Optional CUDA-event timing of every digit-pass launch (bench.py's roofline leg): when enabled,
-// sort_columns_f64 brackets each onesweep_pass_kernel launch with events on the launching stream.
+// sort_columns_f64 brackets each partition_pass_kernel launch with events on the launching stream.
 void sort_profile_enable(bool on);
 // Drains the recorded events (synchronises them): number of pass launches, their total
 // duration in ms and the number of keys they moved.
 void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys);
 
-// Sort `ncols` columns of n doubles each; column c starts at in + c*col_stride and its rows are
-// row_stride elements apart.  On return (stream order) column c's sorted keys/rows are in
-// buffer plan[c].final_buf (1 = A, 2 = B).  error_flag[1] is set if any input is NaN.
+// Sort `ncols` columns of n doubles each on their `window_bits`-bit window (see above); column c
+// starts at in + c*col_stride and its rows are row_stride elements apart.  On return (stream
+// order) column c's keys/rows, ordered by window value, are in buffer plan[c].final_buf
+// (1 = A, 2 = B).  error_flag[kFlagNaN] is set if any input is NaN.
 int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, uint32_t n,
-                     int ncols, const SortBuffers& buf, bool use_lookback, cudaStream_t stream);
+                     int ncols, int window_bits, const SortBuffers& buf, bool use_lookback,
+                     cudaStream_t stream);
 
-// "Scatter by row" that follows each sort: out[col][rows[p] * row_stride] = value[p], where
-// rows[] is the sorted payload (vals[final]) and value[] was staged by the caller in keys[other].
-// For long columns it runs as a partition pass into <= 256 L2-sized row windows followed by a
-// window-local scatter (see sort.cu); short columns are scattered directly.
+// "Scatter by row" that follows each sort: out[col][rows[p] * row_stride] = value[p], where the
+// caller staged rows[] in vals[other] and value[] in keys[other] ("other" = the buffer that is
+// not plan[c].final_buf).  For long columns it runs as a partition pass into <= 256 L2-sized row
+// windows followed by a window-local scatter (see sort.cu); short columns are scattered directly.
 int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
                    int64_t col_stride, bool use_lookback, cudaStream_t stream);
 

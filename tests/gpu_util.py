@@ -64,8 +64,23 @@ def run_stages(X, C_target, col_batch=0):
     dY = DeviceArray(Y)
     rs, cs = (s // 8 for s in X.strides)
     h = plan.handle
-    out = {}
     chk = _lib.check
+    for attempt in range(2):
+        out = _run_stages_once(lib, chk, plan, h, dX, dY, rs, cs, N, K)
+        if out["status"] != 6:  # PBL_RETRY: the plan switched to the 64-bit sort, run again
+            break
+    out["attempts"] = attempt + 1
+    _lib.check(lib.pbl_memcpy_d2h(Y.ctypes.data, dY.ptr, Y.nbytes, None))
+    _lib.check(lib.pbl_stream_synchronize(None))
+    out["result"] = Y
+    dX.free()
+    dY.free()
+    plan.close()
+    return out
+
+
+def _run_stages_once(lib, chk, plan, h, dX, dY, rs, cs, N, K):
+    out = {}
     chk(lib.pbl_ic_stage_begin(h, None))
     chk(lib.pbl_ic_stage_rank_scores(h, dX.ptr, rs, cs, 0, K, None))
     out["scores"] = read_device(plan.buffer(0)[0], (N, K), order="F")
@@ -80,12 +95,6 @@ def run_stages(X, C_target, col_batch=0):
     out["correlated"] = read_device(plan.buffer(0)[0], (N, K), order="F")
     chk(lib.pbl_ic_stage_rank_gather(h, dY.ptr, rs, cs, 0, K, None))
     out["status"] = chk(lib.pbl_ic_stage_status(h, None))
-    _lib.check(lib.pbl_memcpy_d2h(Y.ctypes.data, dY.ptr, Y.nbytes, None))
-    _lib.check(lib.pbl_stream_synchronize(None))
-    out["result"] = Y
-    dX.free()
-    dY.free()
-    plan.close()
     return out
 
 

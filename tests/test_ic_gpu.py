@@ -96,6 +96,40 @@ def test_heavy_ties_partitioned_scatter():
     np.testing.assert_array_equal(got, want)
 
 
+def test_dense_cluster_falls_back_to_full_sort():
+    """Distinct values packed more densely than 2^-40 of the column's range: the 40-bit sort window
+    cannot separate them, the post-sort kernel raises the retry flag and the plan repeats the
+    transform with the exact 64-bit sort.  Output must still be bit-exact."""
+    from probabilit_b200 import ImanConover
+
+    rng = np.random.default_rng(12)
+    n, k = 40_000, 3
+    X = np.asfortranarray(rng.normal(size=(n, k)))
+    X[: n // 2, 1] = 1.0 + rng.permutation(n // 2) * 2.0 ** -52  # n/2 distinct neighbours of 1.0
+    X[n // 2:, 1] = np.exp(rng.uniform(-600, 600, n - n // 2))   # huge dynamic range
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got_stages = gpu_util.run_stages(X, C)
+    assert got_stages["attempts"] == 2 and got_stages["status"] == 0
+    np.testing.assert_array_equal(got_stages["result"], want)
+    np.testing.assert_array_equal(ImanConover().set_target(C)(X), want)
+
+
+def test_window_collisions_are_completed_in_tile():
+    """Many short runs of distinct keys sharing a 40-bit window value (no fallback needed)."""
+    rng = np.random.default_rng(13)
+    n, k = 150_000, 2
+    X = np.asfortranarray(rng.normal(size=(n, k)))
+    base = np.exp(rng.uniform(-300, 300, n // 8))
+    # groups of 8 distinct neighbours (1 ulp apart) around values spread over a huge range
+    X[: (n // 8) * 8, 0] = (base[:, None] * (1.0 + np.arange(8)[None, :] * 2.0 ** -52)).ravel()
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got = gpu_util.run_stages(X, C)
+    assert got["attempts"] == 1 and got["status"] == 0
+    np.testing.assert_array_equal(got["result"], want)
+
+
 def test_c_order_and_column_batches():
     from probabilit_b200 import ImanConover
 
