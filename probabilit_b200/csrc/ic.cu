@@ -96,7 +96,6 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* s_end = s_start + kPostTile;                     // [kPostTile]
   uint32_t* s_w = s_end + kPostTile;                         // [8]
   uint32_t* s_lohi = s_w + 8;                                // [2]
-  double* s_val = reinterpret_cast<double*>(s_raw);          // [kPostTile + 2], reuses s_raw
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
@@ -125,42 +124,44 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   __syncthreads();
 
   // ---- (1) complete the order inside runs of equal window values ----
+  const int lo_i = (int)max((int64_t)0, -wbase);                  // first slot inside the column
+  const int hi_i = (int)min((int64_t)kWin, (int64_t)n - wbase);   // one past the last such slot
   int retry = 0;
   for (int i = tid; i < kWin; i += kPostBlock) {
-    const int64_t g = wbase + i;
-    if (g < 0 || g >= (int64_t)n) continue;
+    if (i < lo_i || i >= hi_i) continue;
     const uint64_t my = s_raw[i];
-    const uint64_t mw = window_value(my, map);
-    uint32_t cnt = 0;
-    int L = 0, R = 0;
-    bool diff = false, open = false;
-    for (int j = i - 1;; --j) {
-      if (j < 0) { open = (wbase + j >= 0); break; }          // unseen element left of the window
-      if (wbase + j < 0) break;                               // start of the column
-      const uint64_t kj = s_raw[j];
-      if (window_value(kj, map) != mw) break;
-      if (L == kHalo) { open = true; break; }
-      cnt += (kj <= my) ? 1u : 0u;                            // equal keys keep their order
-      diff |= (kj != my);
-      ++L;
-    }
-    for (int j = i + 1;; ++j) {
-      if (j >= kWin) { open |= (wbase + j < (int64_t)n); break; }
-      if (wbase + j >= (int64_t)n) break;                     // end of the column
-      const uint64_t kj = s_raw[j];
-      if (window_value(kj, map) != mw) break;
-      if (R == kHalo) { open = true; break; }
-      cnt += (kj < my) ? 1u : 0u;
-      diff |= (kj != my);
-      ++R;
-    }
-    if (L + R + 1 > kHalo - 1) open = true;  // every member of the run must reach the same verdict
     int dst = i;
-    if (diff) {
-      if (!open) {
-        dst = i - L + (int)cnt;
-      } else if (i + R >= kHalo - 1 && i - L <= kHalo + (int)nvalid) {
-        retry = 1;  // cannot be completed here and it matters for this tile's output
+    const bool sl = i > lo_i && same_window(my, s_raw[i - 1], map);
+    const bool sr = i + 1 < hi_i && same_window(my, s_raw[i + 1], map);
+    if (sl || sr || (i == 0 && lo_i == 0 && wbase > 0) || (i == kWin - 1 && wbase + kWin < (int64_t)n)) {
+      uint32_t cnt = 0;
+      int L = 0, R = 0;
+      bool diff = false, open = false;
+      for (int j = i - 1;; --j) {
+        if (j < lo_i) { open = (j < 0 && wbase + j >= 0); break; }  // unseen element left of the window?
+        const uint64_t kj = s_raw[j];
+        if (!same_window(kj, my, map)) break;
+        if (L == kHalo) { open = true; break; }
+        cnt += (kj <= my) ? 1u : 0u;                                // equal keys keep their order
+        diff |= (kj != my);
+        ++L;
+      }
+      for (int j = i + 1;; ++j) {
+        if (j >= hi_i) { open |= (j >= kWin && wbase + j < (int64_t)n); break; }
+        const uint64_t kj = s_raw[j];
+        if (!same_window(kj, my, map)) break;
+        if (R == kHalo) { open = true; break; }
+        cnt += (kj < my) ? 1u : 0u;
+        diff |= (kj != my);
+        ++R;
+      }
+      if (L + R + 1 > kHalo - 1) open = true;  // every member of the run must reach the same verdict
+      if (diff) {
+        if (!open) {
+          dst = i - L + (int)cnt;
+        } else if (i + R >= kHalo - 1 && i - L <= kHalo + (int)nvalid) {
+          retry = 1;  // cannot be completed here and it matters for this tile's output
+        }
       }
     }
     s_key[dst] = my;
@@ -169,16 +170,16 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   if (retry) flags[kFlagWindowRetry] = 1u;
   __syncthreads();
 
-  // values with a one-element halo on both sides; NaN outside the column (never ties)
-  for (uint32_t q = tid; q < nvalid + 2; q += kPostBlock) {
-    int64_t g = (int64_t)tile_start + q - 1;
-    double v = __longlong_as_double(0x7FF8000000000000LL);
-    if (g >= 0 && g < (int64_t)n) v = key_to_double(s_key[kHalo - 1 + q]);
-    s_val[q] = v;
-  }
-  __syncthreads();
+  // ---- (2) tie runs.  teq(q): tile position q holds the same value as position q-1
+  //      (q = 0 .. nvalid; positions outside the column never tie).  Keys are canonical
+  //      (-0.0 folded onto +0.0), so key equality is value equality. ----
+  auto teq = [&](uint32_t q) -> bool {
+    const int64_t g = (int64_t)tile_start + q;  // global index of position q
+    if (g <= 0 || g >= (int64_t)n) return false;
+    return s_key[kHalo + q] == s_key[kHalo + q - 1];
+  };
   int tie = 0;
-  for (uint32_t i = tid; i <= nvalid; i += kPostBlock) tie |= (s_val[i] == s_val[i + 1]);
+  for (uint32_t q = tid; q <= nvalid; q += kPostBlock) tie |= teq(q) ? 1 : 0;
   tie = __syncthreads_or(tie);
 
   if (tie) {
@@ -189,7 +190,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
     for (int i = 0; i < kPostItems; ++i) {
       uint32_t p = tid * kPostItems + i;
       uint32_t v = 0;
-      if (p < nvalid && !(s_val[p] == s_val[p + 1])) v = tile_start + p + 1;  // head: pos+1
+      if (p < nvalid && !teq(p)) v = tile_start + p + 1;  // head: pos+1
       run = max(run, v);
       st[i] = run;
     }
@@ -199,7 +200,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
     for (int i = kPostItems - 1; i >= 0; --i) {
       uint32_t p = tid * kPostItems + i;
       uint32_t v = 0xFFFFFFFFu;
-      if (p < nvalid && !(s_val[p + 1] == s_val[p + 2])) v = tile_start + p;  // tail: pos
+      if (p < nvalid && !teq(p + 1)) v = tile_start + p;  // tail: pos
       run = min(run, v);
       en[i] = run;
     }
@@ -208,7 +209,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
     // (valid because such a run is pure: any impure long run has raised kFlagWindowRetry)
     if (tid == 0) {
       uint32_t lo = tile_start, hi = tile_start + nvalid - 1;
-      if (s_val[0] == s_val[1]) {
+      if (teq(0)) {
         const uint64_t w = window_value(s_key[kHalo], map);
         uint32_t a = 0, b = tile_start;  // first q in [0, tile_start) with window(q) >= w
         while (a < b) {
@@ -217,7 +218,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
         }
         lo = a;
       }
-      if (s_val[nvalid] == s_val[nvalid + 1]) {
+      if (teq(nvalid)) {
         const uint64_t w = window_value(s_key[kHalo + nvalid - 1], map);
         uint32_t a = tile_start + nvalid, b = n;  // first q with window(q) > w
         while (a < b) {
@@ -259,7 +260,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
         double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
         double q = __ddiv_rn(avg, (double)((uint64_t)n + 1ull));
         stage[g] = ndtri(q);
-        sx[g] = (row & kNegZeroFlag) ? -0.0 : s_val[p + 1];
+        sx[g] = (row & kNegZeroFlag) ? -0.0 : key_to_double(s_key[kHalo + p]);
       } else {
         uint32_t m = s + (e - s) / 2;
         stage[g] = sx[m];

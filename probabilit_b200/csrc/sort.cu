@@ -81,9 +81,9 @@ col_minmax_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t co
 
 // --------------------------------------------------------------------------------------
 // Kernel 1: the digit histograms of every column's window values in one read of the input
-// (8 B / key).  Shared-memory atomics; the two most significant digits (few distinct values for
-// real data, i.e. same-address conflicts) are warp-aggregated with match.any, which is cheap
-// exactly when few distinct values are present.
+// (8 B / key).  Shared-memory atomics; the most significant digit (few distinct values for real
+// data, i.e. same-address conflicts) is warp-aggregated with match.any, which is cheap exactly
+// when few distinct values are present.
 // --------------------------------------------------------------------------------------
 template <int BLOCK, int UNROLL, int NP>
 __global__ void __launch_bounds__(BLOCK)
@@ -113,15 +113,11 @@ sort_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col
     for (int u = 0; u < UNROLL; ++u) {
       if (valid[u]) {
 #pragma unroll
-        for (int p = 0; p < NP - 2; ++p) atomicAdd(&sh[p][(uint32_t)(w[u] >> (8 * p)) & 255u], 1u);
+        for (int p = 0; p < NP - 1; ++p) atomicAdd(&sh[p][(uint32_t)(w[u] >> (8 * p)) & 255u], 1u);
       }
-      uint32_t top = valid[u] ? (uint32_t)(w[u] >> (8 * (NP - 2))) & 0xFFFFu : 0xFFFFFFFFu;
+      uint32_t top = valid[u] ? (uint32_t)(w[u] >> (8 * (NP - 1))) & 0xFFu : 0xFFFFFFFFu;
       uint32_t m = __match_any_sync(0xFFFFFFFFu, top);
-      if (valid[u] && lane == (uint32_t)(__ffs(m) - 1)) {
-        uint32_t c = __popc(m);
-        atomicAdd(&sh[NP - 2][top & 255u], c);
-        atomicAdd(&sh[NP - 1][top >> 8], c);
-      }
+      if (valid[u] && lane == (uint32_t)(__ffs(m) - 1)) atomicAdd(&sh[NP - 1][top], (uint32_t)__popc(m));
     }
   }
   __syncthreads();
@@ -487,9 +483,28 @@ partition_pass_kernel(const PassArgs a) {
     uint32_t excl = 0;
     if (a.use_lookback) {
       if (tile != 0) {
+        // the 4 nearest predecessors are fetched together (one L2 round trip instead of up to 4)
+        constexpr int LB = 4;
+        uint32_t pre[LB];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+          int64_t t = (int64_t)tile - 1 - i;
+          pre[i] = (t >= 0) ? ld_relaxed_u32(&st[(size_t)t * kRadix + tid]) : kFlagInclusive;
+        }
         int64_t t = (int64_t)tile - 1;
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+          if (!done) {
+            uint32_t w = pre[i];
+            if ((w & (kFlagInclusive | kFlagPartial)) == 0) break;  // not published yet: poll below
+            excl += w & kValueMask;
+            if (w & kFlagInclusive) done = true;
+            --t;
+          }
+        }
         uint32_t spins = 0;
-        while (true) {
+        while (!done) {
           uint32_t w = ld_relaxed_u32(&st[(size_t)t * kRadix + tid]);
           if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
             if (++spins > kSpinLimit) {

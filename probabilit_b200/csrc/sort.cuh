@@ -61,7 +61,9 @@ struct PassPlan {
   uint8_t pad[7];
 };
 
-// Monotone map key -> window value:  (key - kmin) >> sh  fits in window_bits bits.
+// Monotone map key -> window value:  (key - kmin) >> sh, with kmin a multiple of 2^sh, fits in
+// window_bits bits.  Because kmin is aligned, two keys share a window value iff
+// ((a ^ b) >> sh) == 0.
 struct KeyMap {
   uint64_t kmin;
   uint32_t sh;
@@ -75,13 +77,19 @@ __device__ __forceinline__ KeyMap load_key_map(const uint64_t* __restrict__ kmin
     const uint64_t lo = kminmax[2 * col], hi = kminmax[2 * col + 1];
     const uint64_t range = hi >= lo ? hi - lo : 0;
     const int bits = 64 - __clzll((long long)range);
-    m.kmin = lo;
-    m.sh = bits > window_bits ? (uint32_t)(bits - window_bits) : 0u;
+    uint32_t sh = bits > window_bits ? (uint32_t)(bits - window_bits) : 0u;
+    // aligning kmin down can widen the span by one window value: make sure it still fits
+    if ((((hi >> sh) - (lo >> sh)) >> window_bits) != 0) ++sh;
+    m.sh = sh;
+    m.kmin = (lo >> sh) << sh;
   }
   return m;
 }
 __device__ __forceinline__ uint64_t window_value(uint64_t key, const KeyMap& m) {
   return (key - m.kmin) >> m.sh;
+}
+__device__ __forceinline__ bool same_window(uint64_t a, uint64_t b, const KeyMap& m) {
+  return ((a ^ b) >> m.sh) == 0;
 }
 
 struct SortBuffers {
