@@ -28,12 +28,12 @@ namespace {
 // post-sort kernel: tie runs on the sorted column, then either scores (MODE 0) or the gather
 // of the sorted marginal (MODE 1)
 // ======================================================================================
-constexpr int kPostBlock = 256;
-constexpr int kPostItems = 8;
+constexpr int kPostBlock = 512;
+constexpr int kPostItems = 4;
 constexpr int kPostTile = kPostBlock * kPostItems;
 constexpr int kHalo = 64;                      // window values may repeat in runs of < kHalo keys
 constexpr int kWin = kPostTile + 2 * kHalo;
-constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 64;
+constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 128;
 
 __device__ __forceinline__ uint32_t block_excl_prefix_max(uint32_t v, uint32_t* s_w) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -81,12 +81,20 @@ __device__ __forceinline__ uint32_t block_excl_suffix_min(uint32_t v, uint32_t* 
 //              (rankdata(...).astype(int) - 1 then the gather, correlation.py:422-423)
 //  (3) stages value and row, in sorted order, in the "other" ping-pong buffer (the one that does
 //      not hold the sorted keys); scatter_by_row (sort.cu) then delivers value -> row.
+// van der Waerden scores of an untied column in sorted order: vdw[p] = ndtri((p+1)/(n+1)).
+// They depend on n only, so the table is built once per plan and shared by all columns
+// (the per-element ndtri -- several fp64 divisions, log, sqrt -- is then paid for ties only).
+__global__ void __launch_bounds__(256) vdw_table_kernel(uint32_t n, double* __restrict__ vdw) {
+  for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (uint64_t)gridDim.x * 256)
+    vdw[p] = ndtri(__ddiv_rn((double)(p + 1), (double)((uint64_t)n + 1ull)));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kPostBlock)
 post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB,
                  const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
                  int window_bits, uint32_t n, double* __restrict__ sortedX,
-                 uint32_t* __restrict__ flags) {
+                 const double* __restrict__ vdw, uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char psm[];
   uint64_t* s_raw = reinterpret_cast<uint64_t*>(psm);        // [kWin] keys as the sort left them
   uint64_t* s_key = s_raw + kWin;                            // [kWin] completed order
@@ -94,8 +102,8 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* s_row = s_rawv + kWin;                           // [kWin] rows, completed order
   uint32_t* s_start = s_row + kWin;                          // [kPostTile]
   uint32_t* s_end = s_start + kPostTile;                     // [kPostTile]
-  uint32_t* s_w = s_end + kPostTile;                         // [8]
-  uint32_t* s_lohi = s_w + 8;                                // [2]
+  uint32_t* s_w = s_end + kPostTile;                         // [kPostBlock / 32]
+  uint32_t* s_lohi = s_w + kPostBlock / 32;                  // [2]
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
@@ -257,9 +265,14 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
       const uint32_t row = s_row[kHalo + p];
       rows_out[g] = row & kRowMask;
       if (MODE == 0) {
-        double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
-        double q = __ddiv_rn(avg, (double)((uint64_t)n + 1ull));
-        stage[g] = ndtri(q);
+        double sc;
+        if (s == e) {
+          sc = ld_stream_f64(vdw + g);  // untied: the score depends on the position only
+        } else {
+          double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
+          sc = ndtri(__ddiv_rn(avg, (double)((uint64_t)n + 1ull)));
+        }
+        stage[g] = sc;
         sx[g] = (row & kNegZeroFlag) ? -0.0 : key_to_double(s_key[kHalo + p]);
       } else {
         uint32_t m = s + (e - s) / 2;
@@ -625,6 +638,7 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   A(&p->flags, 8);
   p->sort.error_flag = p->flags;
   A(&p->sortedX, (size_t)k * n);
+  A(&p->vdw, (size_t)n);
   A(&p->scores, (size_t)k * n);
   A(&p->gram, (size_t)k * k);
   A(&p->colsum, (size_t)k);
@@ -661,6 +675,7 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->sort.kminmax);
   cudaFree(p->flags);
   cudaFree(p->sortedX);
+  cudaFree(p->vdw);
   cudaFree(p->scores);
   cudaFree(p->gram);
   cudaFree(p->colsum);
@@ -695,6 +710,11 @@ static int post_sort_attr() {
 int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream) {
   const uint32_t n = (uint32_t)p->n;
+  if (!p->vdw_ready) {
+    vdw_table_kernel<<<(unsigned)std::min<int64_t>((p->n + 255) / 256, (int64_t)num_sms() * 16), 256, 0, stream>>>(n, p->vdw);
+    PBL_LAUNCH_CHECK();
+    p->vdw_ready = true;
+  }
   for (int c = col0; c < col0 + ncols; c += p->col_batch) {
     int nb = std::min(p->col_batch, col0 + ncols - c);
     PBL_RETURN_IF(sort_columns_f64(X + (int64_t)c * col_stride, row_stride, col_stride, n, nb,
@@ -703,7 +723,7 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     PBL_RETURN_IF(post_sort_attr());
     post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
         p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->flags);
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
                                  p->use_lookback, stream));
@@ -779,7 +799,7 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_RETURN_IF(post_sort_attr());
     post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
         p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->flags);
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
                                  col_stride, p->use_lookback, stream));

@@ -17,6 +17,8 @@ struct IcPlan {
 
   SortBuffers sort;            // sized for col_batch columns
   double* sortedX = nullptr;   // [k][n]  np.sort(X[:,c])
+  double* vdw = nullptr;       // [n] ndtri((p+1)/(n+1)): scores of an untied column, sorted order
+  bool vdw_ready = false;
   double* scores = nullptr;    // [k][n]  van der Waerden scores, then (in place) correlated scores
   double* gram_partials = nullptr;
   int gram_row_blocks = 0;
