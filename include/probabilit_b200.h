@@ -63,6 +63,10 @@ typedef struct pbl_ic_plan pbl_ic_plan;
 /* Workspace for (n, k) problems on the current device.  col_batch <= 0: choose automatically
  * (columns sorted per launch batch; bounds the sort workspace). */
 PBL_API int pbl_ic_plan_create(int64_t n, int32_t k, int32_t col_batch, pbl_ic_plan** plan);
+/* flags bit 0 (PBL_IC_ROWS_ONLY): no sort workspace -- the plan serves the Gram / solve / transform
+ * stages of a row shard in the multi-GPU driver (the sorts run in a second, column-shard plan). */
+#define PBL_IC_ROWS_ONLY 1
+PBL_API int pbl_ic_plan_create_ex(int64_t n, int32_t k, int32_t col_batch, int32_t flags, pbl_ic_plan** plan);
 PBL_API int pbl_ic_plan_destroy(pbl_ic_plan* plan);
 PBL_API uint64_t pbl_ic_plan_bytes(const pbl_ic_plan* plan);
 

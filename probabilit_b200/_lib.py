@@ -39,6 +39,7 @@ SIGNATURES = {
     "pbl_memcpy_d2h": (C.c_int, [_vp, _vp, _u64, _vp]),
     "pbl_stream_synchronize": (C.c_int, [_vp]),
     "pbl_ic_plan_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_vp)]),
+    "pbl_ic_plan_create_ex": (C.c_int, [_i64, _i32, _i32, _i32, C.POINTER(_vp)]),
     "pbl_ic_plan_destroy": (C.c_int, [_vp]),
     "pbl_ic_plan_bytes": (_u64, [_vp]),
     "pbl_ic_plan_set_target": (C.c_int, [_vp, _pd]),

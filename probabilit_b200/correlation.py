@@ -82,12 +82,14 @@ def _strides_elems(shape, strides_bytes, itemsize):
 class _IcPlan:
     """Owns one pbl_ic_plan (device workspace for an (n, k) problem on one device)."""
 
-    def __init__(self, n, k, device, col_batch=0):
+    def __init__(self, n, k, device, col_batch=0, rows_only=False):
         self.lib = _lib.require_gpu()
         self.n, self.k, self.device = n, k, device
         _lib.check(self.lib.pbl_set_device(device), "pbl_set_device")
         h = C.c_void_p()
-        st = _lib.check(self.lib.pbl_ic_plan_create(n, k, col_batch, C.byref(h)), "pbl_ic_plan_create")
+        st = _lib.check(
+            self.lib.pbl_ic_plan_create_ex(n, k, col_batch, 1 if rows_only else 0, C.byref(h)),
+            "pbl_ic_plan_create")
         if st != _lib.STATUS_OK:
             raise ValueError(_lib.last_error())
         self.handle = h

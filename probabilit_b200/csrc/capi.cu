@@ -81,13 +81,17 @@ int pbl_stream_synchronize(void* stream) {
 }
 
 // ---------------------------------------------------------------------------- Iman-Conover
-int pbl_ic_plan_create(int64_t n, int32_t k, int32_t col_batch, pbl_ic_plan** plan) {
+int pbl_ic_plan_create_ex(int64_t n, int32_t k, int32_t col_batch, int32_t flags, pbl_ic_plan** plan) {
   if (!plan) return kBadShape;
   *plan = nullptr;
   pbl::IcPlan* impl = nullptr;
-  PBL_RETURN_IF(pbl::ic_plan_create(n, k, col_batch, &impl));
+  PBL_RETURN_IF(pbl::ic_plan_create(n, k, col_batch, flags, &impl));
   *plan = new pbl_ic_plan{impl};
   return kOk;
+}
+
+int pbl_ic_plan_create(int64_t n, int32_t k, int32_t col_batch, pbl_ic_plan** plan) {
+  return pbl_ic_plan_create_ex(n, k, col_batch, 0, plan);
 }
 
 int pbl_ic_plan_destroy(pbl_ic_plan* plan) {

@@ -594,7 +594,7 @@ int gram_tg_for(int k) { return k <= 16 ? 4 : (k <= 32 ? 8 : 16); }
 // ======================================================================================
 // plan
 // ======================================================================================
-int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
+int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
   *out = nullptr;
   if (n < 1 || k < 1 || n > (int64_t)kMaxSortN || k > 8192) {
     set_last_error("ic_plan_create: need 1 <= n < 2^30 and 1 <= k <= 8192");
@@ -603,6 +603,7 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   IcPlan* p = new IcPlan();
   p->n = n;
   p->k = k;
+  p->rows_only = (flags & 1) != 0;
   PBL_CUDA_CHECK(cudaGetDevice(&p->device));
   const char* lb = getenv("PBL_SORT_LOOKBACK");
   p->use_lookback = !(lb && lb[0] == '0');
@@ -626,19 +627,21 @@ int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out) {
   auto A = [&](auto** ptr, size_t count) {
     if (rc == kOk) rc = dev_alloc(ptr, count, p);
   };
-  A(&p->sort.keysA, (size_t)cb * n);
-  A(&p->sort.keysB, (size_t)cb * n);
-  A(&p->sort.valsA, (size_t)cb * n);
-  A(&p->sort.valsB, (size_t)cb * n);
-  A(&p->sort.hist, (size_t)cb * kMaxPasses * kRadix);
-  A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
-  A(&p->sort.tile_counter, (size_t)cb * (kMaxPasses + 1));
-  A(&p->sort.kminmax, (size_t)cb * 2);
-  A(&p->sort.plan, (size_t)cb);
+  if (!p->rows_only) {
+    A(&p->sort.keysA, (size_t)cb * n);
+    A(&p->sort.keysB, (size_t)cb * n);
+    A(&p->sort.valsA, (size_t)cb * n);
+    A(&p->sort.valsB, (size_t)cb * n);
+    A(&p->sort.hist, (size_t)cb * kMaxPasses * kRadix);
+    A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
+    A(&p->sort.tile_counter, (size_t)cb * (kMaxPasses + 1));
+    A(&p->sort.kminmax, (size_t)cb * 2);
+    A(&p->sort.plan, (size_t)cb);
+    A(&p->sortedX, (size_t)k * n);
+    A(&p->vdw, (size_t)n);
+  }
   A(&p->flags, 8);
   p->sort.error_flag = p->flags;
-  A(&p->sortedX, (size_t)k * n);
-  A(&p->vdw, (size_t)n);
   A(&p->scores, (size_t)k * n);
   A(&p->gram, (size_t)k * k);
   A(&p->colsum, (size_t)k);
@@ -709,6 +712,10 @@ static int post_sort_attr() {
 
 int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream) {
+  if (p->rows_only) {
+    set_last_error("this plan was created without a sort workspace (rows-only)");
+    return kBadShape;
+  }
   const uint32_t n = (uint32_t)p->n;
   if (!p->vdw_ready) {
     vdw_table_kernel<<<(unsigned)std::min<int64_t>((p->n + 255) / 256, (int64_t)num_sms() * 16), 256, 0, stream>>>(n, p->vdw);
@@ -790,6 +797,10 @@ int ic_stage_transform(IcPlan* p, cudaStream_t stream) {
 
 int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_stride, int col0,
                          int ncols, cudaStream_t stream) {
+  if (p->rows_only) {
+    set_last_error("this plan was created without a sort workspace (rows-only)");
+    return kBadShape;
+  }
   const uint32_t n = (uint32_t)p->n;
   for (int c = col0; c < col0 + ncols; c += p->col_batch) {
     int nb = std::min(p->col_batch, col0 + ncols - c);

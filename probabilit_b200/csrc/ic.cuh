@@ -14,6 +14,7 @@ struct IcPlan {
   bool use_lookback = true;
   int window_bits = 40;  // sort window (sort.cuh); switches to 64 after a kRetry status
   bool has_target = false;
+  bool rows_only = false;  // no sort workspace: Gram / solve / transform stages only (multi-GPU row shard)
 
   SortBuffers sort;            // sized for col_batch columns
   double* sortedX = nullptr;   // [k][n]  np.sort(X[:,c])
@@ -32,7 +33,8 @@ struct IcPlan {
   size_t bytes = 0;            // device bytes held by the plan
 };
 
-int ic_plan_create(int64_t n, int k, int col_batch, IcPlan** out);
+// flags bit 0: rows-only plan (see IcPlan::rows_only)
+int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out);
 void ic_plan_destroy(IcPlan* plan);
 int ic_plan_set_target(IcPlan* plan, const double* P_lower_host);
 
