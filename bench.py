@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=lambda s: int(float(s)), default=100_000_000)
+    ap.add_argument("--rows", dest="n", type=lambda s: int(float(s)), default=100_000_000)
     ap.add_argument("--d", type=int, default=16)
     ap.add_argument("--col-batch", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=2)
