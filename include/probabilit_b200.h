@@ -109,6 +109,41 @@ PBL_API int pbl_ic_stage_status(pbl_ic_plan* plan, void* stream);
  * 3 colsum [k], 4 T [k][k] row-major, 5 work (R then Q) [k][k]. */
 PBL_API int pbl_ic_plan_buffer(pbl_ic_plan* plan, int32_t what, void** ptr_dev, uint64_t* bytes);
 
+/* ---- unit-cube generators: the `quantiles = ...` draw of Node.sample, src/probabilit/modeling.py:479-489.
+ * out_dev is (n, d) fp64 addressed with element strides (column-major: row_stride 1, col_stride n).
+ * Every point depends on its global row index only: a row shard passes its first row as
+ * row0 / skip / start_index and needs no communication. ---- */
+
+/* method=None: random_state.random((n, d)), modeling.py:485-486.  Philox4x32-10 counter stream
+ * (statistical parity with NumPy's generators, not bit parity); row0 must be even. */
+PBL_API int pbl_uniform_f64(uint64_t seed, uint64_t row0, int64_t n, int32_t d, double* out_dev,
+                            int64_t row_stride, int64_t col_stride, void* stream);
+
+/* method="sobol": scipy.stats.qmc.Sobol(d, rng).random(n), modeling.py:482,488-489.
+ *   direction numbers: Joe-Kuo tables (poly[d], vinit[d][vinit_cols], int64) -> sv[d][bits]
+ *   scramble: LMS + digital shift from the host generator's random bits (ltm_bits[d][bits][bits],
+ *             shift_bits[d][bits], one byte per bit, drawn exactly like scipy draws them)
+ *   points skip .. skip+n-1 of the sequence; bit-exact with scipy for the same sv / shift. */
+PBL_API int pbl_sobol_direction_numbers(const int64_t* poly_dev, const int64_t* vinit_dev, int32_t vinit_cols,
+                                        int32_t d, int32_t bits, uint64_t* sv_dev, void* stream);
+PBL_API int pbl_sobol_scramble(const uint8_t* ltm_bits_dev, const uint8_t* shift_bits_dev, int32_t d,
+                               int32_t bits, uint64_t* sv_dev, uint64_t* shift_dev, void* stream);
+PBL_API int pbl_sobol_f64(const uint64_t* sv_dev, const uint64_t* shift_dev, int32_t d, int32_t bits,
+                          uint64_t skip, int64_t n, double* out_dev, int64_t row_stride,
+                          int64_t col_stride, void* stream);
+
+/* method="halton": scipy.stats.qmc.Halton(d, rng).random(n), modeling.py:481.  bases[d] = first d
+ * primes; perms (or NULL when unscrambled): per dimension perm_count[c] x bases[c] digit
+ * permutations starting at perms[perm_off[c]].  Bit-exact with scipy for the same permutations. */
+PBL_API int pbl_halton_f64(const int32_t* bases_dev, const int64_t* perms_dev, const int64_t* perm_off_dev,
+                           const int32_t* perm_count_dev, int32_t d, uint64_t start_index, int64_t n,
+                           double* out_dev, int64_t row_stride, int64_t col_stride, void* stream);
+
+/* method="lhs": scipy.stats.qmc.LatinHypercube(d, rng).random(n), modeling.py:480 / README.md:113.
+ * (perm + 1 - U) / n with a counter-based per-column permutation (statistical parity). */
+PBL_API int pbl_lhs_f64(uint64_t seed, int64_t n, int32_t d, int32_t scramble, double* out_dev,
+                        int64_t row_stride, int64_t col_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

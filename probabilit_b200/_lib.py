@@ -53,6 +53,12 @@ SIGNATURES = {
     "pbl_ic_stage_rank_gather": (C.c_int, [_vp, _pd, _i64, _i64, _i32, _i32, _vp]),
     "pbl_ic_stage_status": (C.c_int, [_vp, _vp]),
     "pbl_ic_plan_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_u64)]),
+    "pbl_uniform_f64": (C.c_int, [_u64, _u64, _i64, _i32, _pd, _i64, _i64, _vp]),
+    "pbl_sobol_direction_numbers": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "pbl_sobol_scramble": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "pbl_sobol_f64": (C.c_int, [_vp, _vp, _i32, _i32, _u64, _i64, _pd, _i64, _i64, _vp]),
+    "pbl_halton_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _u64, _i64, _pd, _i64, _i64, _vp]),
+    "pbl_lhs_f64": (C.c_int, [_u64, _i64, _i32, _i32, _pd, _i64, _i64, _vp]),
 }
 
 

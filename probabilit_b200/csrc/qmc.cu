@@ -1,0 +1,317 @@
+// Unit-cube generators: (n, d) fp64 in [0, 1), written as N x d tiles with coalesced (and, for
+// unit row stride, 128-bit) stores.  They replace the generator calls of the reference's
+// Node.sample (src/probabilit/modeling.py:479-489):
+//   method None      random_state.random((n, d))          -> philox_uniform_kernel (statistical parity)
+//   method "sobol"   scipy.stats.qmc.Sobol(d, rng).random  -> sobol_* kernels        (bit-exact)
+//   method "halton"  scipy.stats.qmc.Halton(d, rng).random -> halton_kernel         (bit-exact)
+//   method "lhs"     scipy.stats.qmc.LatinHypercube        -> lhs_kernel            (statistical parity)
+// Every point is a pure function of its row index, so row shards on several GPUs need no
+// communication (skip-ahead = start the index at the shard's first row).
+#include "../../include/probabilit_b200.h"
+#include "common.cuh"
+
+namespace pbl {
+namespace {
+
+// ------------------------------------------------------------------------------ Philox4x32-10
+struct U4 {
+  uint32_t x, y, z, w;
+};
+__device__ __forceinline__ U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    U4 n;
+    n.x = hi1 ^ ctr.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ ctr.w ^ k1;
+    n.w = lo0;
+    ctr = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return ctr;
+}
+// 53-bit uniform in [0, 1) from two 32-bit words (the construction NumPy uses for its doubles)
+__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// one thread: rows (2t, 2t+1) of one column
+__global__ void __launch_bounds__(256)
+philox_uniform_kernel(uint64_t seed, uint64_t row0, int64_t n, int32_t d, double* __restrict__ out,
+                      int64_t row_stride, int64_t col_stride) {
+  const int c = blockIdx.y;
+  const int64_t pair = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r = pair * 2;
+  if (r >= n) return;
+  const uint64_t g = row0 + (uint64_t)r;  // global row of the first of the two
+  U4 ctr = {(uint32_t)(g >> 1), (uint32_t)(g >> 33), (uint32_t)c, 0x50424C31u};
+  U4 o = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  // the counter is per *pair of global rows*: shard boundaries must be even (the host checks)
+  double a = u01_53(o.x, o.y), b = u01_53(o.z, o.w);
+  double* p = out + (int64_t)c * col_stride + r * row_stride;
+  if (row_stride == 1 && r + 1 < n && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  } else {
+    p[0] = a;
+    if (r + 1 < n) p[row_stride] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------ Sobol'
+// scipy.stats._sobol._initialize_v: Joe-Kuo direction numbers, one thread per dimension.
+__global__ void sobol_direction_kernel(const int64_t* __restrict__ poly, const int64_t* __restrict__ vinit,
+                                       int32_t vinit_cols, int32_t d, int32_t bits,
+                                       uint64_t* __restrict__ sv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  uint64_t v[64];
+  if (i == 0) {
+    for (int j = 0; j < bits; ++j) v[j] = 1;
+  } else {
+    const uint64_t p = (uint64_t)poly[i];
+    const int m = 63 - __clzll((long long)p);
+    for (int j = 0; j < bits; ++j) v[j] = 0;
+    for (int j = 0; j < m && j < bits; ++j) v[j] = (uint64_t)vinit[(size_t)i * vinit_cols + j];
+    for (int j = m; j < bits; ++j) {
+      uint64_t nv = v[j - m];
+      for (int k = 0; k < m; ++k)
+        if ((p >> (m - 1 - k)) & 1ull) nv ^= (2ull << k) * v[j - k - 1];
+      v[j] = nv;
+    }
+  }
+  for (int j = 0; j < bits; ++j) sv[(size_t)i * bits + j] = v[j] << (bits - 1 - j);
+}
+
+// LMS scramble (scipy.stats._sobol._cscramble): sv[i][j] <- L_i * sv[i][j] over GF(2), bit
+// vectors MSB first, L_i lower triangular with unit diagonal built from the host's random bits;
+// shift[i] = sum_b shift_bits[i][b] << b.  One thread per (dimension, column j).
+__global__ void sobol_scramble_kernel(const uint8_t* __restrict__ ltm_bits, const uint8_t* __restrict__ shift_bits,
+                                      int32_t d, int32_t bits, uint64_t* __restrict__ sv,
+                                      uint64_t* __restrict__ shift) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d * bits) return;
+  const int i = t / bits, j = t % bits;
+  const uint64_t vdj = sv[(size_t)i * bits + j];
+  uint64_t t2 = 0;
+  for (int p = 0; p < bits; ++p) {
+    uint64_t row = 0;
+    for (int k = 0; k <= p; ++k) {
+      uint64_t bit = (k == p) ? 1ull : (uint64_t)(ltm_bits[((size_t)i * bits + p) * bits + k] & 1);
+      row |= bit << (bits - 1 - k);
+    }
+    t2 |= (uint64_t)(__popcll(row & vdj) & 1) << (bits - 1 - p);
+  }
+  __syncthreads();  // all reads of sv by this block are done (blocks never share a (i, j))
+  sv[(size_t)i * bits + j] = t2;
+  if (j == 0) {
+    uint64_t s = 0;
+    for (int b = 0; b < bits; ++b) s |= (uint64_t)(shift_bits[(size_t)i * bits + b] & 1) << b;
+    shift[i] = s;
+  }
+}
+
+// point j = (shift ^ XOR_{b set in gray(j)} sv[b]) * 2^-bits; rows (j, j+1) with j even share all
+// but sv[0].  One thread: two consecutive rows of one dimension.
+__global__ void __launch_bounds__(256)
+sobol_points_kernel(const uint64_t* __restrict__ sv, const uint64_t* __restrict__ shift, int32_t bits,
+                    uint64_t skip, int64_t n, double* __restrict__ out, int64_t row_stride,
+                    int64_t col_stride) {
+  __shared__ uint64_t s_sv[64];
+  const int c = blockIdx.y;
+  if (threadIdx.x < bits) s_sv[threadIdx.x] = sv[(size_t)c * bits + threadIdx.x];
+  __syncthreads();
+  // pairs are aligned to even *global* indices; the first/last pair of a shard may be half used
+  const uint64_t first_pair = skip >> 1;
+  const uint64_t pair = first_pair + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint64_t j0 = pair << 1;
+  if (j0 >= skip + (uint64_t)n) return;
+  uint64_t g = j0 ^ (j0 >> 1);
+  uint64_t q = shift[c];
+  while (g) {
+    int b = __ffsll((long long)g) - 1;
+    q ^= s_sv[b];
+    g &= g - 1;
+  }
+  const double scale = __longlong_as_double((long long)(1023 - bits) << 52);  // 2^-bits
+  const double a = __ull2double_rn(q) * scale;
+  const double b = __ull2double_rn(q ^ s_sv[0]) * scale;
+  const int64_t r0 = (int64_t)(j0 - skip);  // may be -1 for the first pair
+  double* colp = out + (int64_t)c * col_stride;
+  if (r0 >= 0 && r0 + 1 < n && row_stride == 1 &&
+      ((reinterpret_cast<uintptr_t>(colp + r0) & 15) == 0)) {
+    *reinterpret_cast<double2*>(colp + r0) = make_double2(a, b);
+  } else {
+    if (r0 >= 0) colp[r0 * row_stride] = a;
+    if (r0 + 1 < n) colp[(r0 + 1) * row_stride] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------ Halton
+// scipy.stats._qmc_cy._cy_van_der_corput(_scrambled): radical inverse in base b with the same
+// floating-point operation order (no FMA contraction), optional per-digit permutations.
+__global__ void __launch_bounds__(256)
+halton_kernel(const int32_t* __restrict__ bases, const int64_t* __restrict__ perms,
+              const int64_t* __restrict__ perm_off, const int32_t* __restrict__ perm_count,
+              uint64_t start_index, int64_t n, double* __restrict__ out, int64_t row_stride,
+              int64_t col_stride) {
+  const int c = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t base = (uint32_t)bases[c];
+  uint64_t quotient = start_index + (uint64_t)r;
+  const double fb = (double)base;
+  double b2r = __ddiv_rn(1.0, fb);
+  double acc = 0.0;
+  if (perms == nullptr) {
+    while (__dadd_rn(1.0, -b2r) < 1.0) {
+      uint64_t qn = quotient / base;
+      uint32_t rem = (uint32_t)(quotient - qn * base);
+      acc = __dadd_rn(acc, __dmul_rn((double)rem, b2r));
+      b2r = __ddiv_rn(b2r, fb);
+      quotient = qn;
+    }
+  } else {
+    const int64_t* pc = perms + perm_off[c];
+    const int count = perm_count[c];
+    for (int j = 0; j < count; ++j) {
+      uint64_t qn = quotient / base;
+      uint32_t rem = (uint32_t)(quotient - qn * base);
+      acc = __dadd_rn(acc, __dmul_rn((double)pc[(size_t)j * base + rem], b2r));
+      b2r = __ddiv_rn(b2r, fb);
+      quotient = qn;
+    }
+  }
+  out[(int64_t)c * col_stride + r * row_stride] = acc;
+}
+
+// ------------------------------------------------------------------------------ Latin hypercube
+// (perm_c(i) + 1 - u) / n  (scipy/stats/_qmc.py:1546-1559): per-column pseudo-random permutation
+// of 0..n-1 as a keyed Feistel network over the next power of four with cycle walking (a
+// bijection evaluated independently per row: no shuffle pass, no memory traffic), u from Philox.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t i, uint64_t n, int half_bits, uint32_t k0, uint32_t k1) {
+  const uint32_t mask = (half_bits >= 32) ? 0xFFFFFFFFu : ((1u << half_bits) - 1u);
+  uint64_t x = i;
+  do {
+    uint32_t L = (uint32_t)(x >> half_bits) & mask, R = (uint32_t)x & mask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r)) ^ mix32((R >> 7) + k1 + (uint32_t)r);
+      uint32_t nl = R;
+      R = (L ^ f) & mask;
+      L = nl;
+    }
+    x = ((uint64_t)L << half_bits) | R;
+  } while (x >= n);
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+lhs_kernel(uint64_t seed, int64_t n, int scramble, double* __restrict__ out, int64_t row_stride,
+           int64_t col_stride) {
+  const int c = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  int bits = 64 - __clzll((long long)(n - 1 > 0 ? n - 1 : 1));
+  int half = (bits + 1) / 2;
+  if (half < 1) half = 1;
+  U4 kk = philox4x32_10({(uint32_t)c, 0x4C485331u, 0u, 0u}, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint64_t p = feistel_perm((uint64_t)r, (uint64_t)n, half, kk.x, kk.y);
+  double u = 0.5;
+  if (scramble) {
+    U4 o = philox4x32_10({(uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)c, 0x4C485332u},
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+    u = u01_53(o.x, o.y);
+  }
+  out[(int64_t)c * col_stride + r * row_stride] = __ddiv_rn(__dadd_rn((double)(p + 1), -u), (double)n);
+}
+
+}  // namespace
+}  // namespace pbl
+
+using pbl::kBadShape;
+using pbl::kOk;
+
+extern "C" {
+
+int pbl_uniform_f64(uint64_t seed, uint64_t row0, int64_t n, int32_t d, double* out_dev,
+                    int64_t row_stride, int64_t col_stride, void* stream) {
+  if (n < 0 || d < 0 || !out_dev || (row0 & 1)) {
+    pbl::set_last_error("pbl_uniform_f64: bad arguments (row0 must be even)");
+    return kBadShape;
+  }
+  if (n == 0 || d == 0) return kOk;
+  dim3 grid((unsigned)(((n + 1) / 2 + 255) / 256), (unsigned)d);
+  pbl::philox_uniform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, row0, n, d, out_dev, row_stride,
+                                                                   col_stride);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int pbl_sobol_direction_numbers(const int64_t* poly_dev, const int64_t* vinit_dev, int32_t vinit_cols,
+                                int32_t d, int32_t bits, uint64_t* sv_dev, void* stream) {
+  if (d < 1 || bits < 1 || bits > 64 || !poly_dev || !vinit_dev || !sv_dev) return kBadShape;
+  pbl::sobol_direction_kernel<<<(d + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poly_dev, vinit_dev, vinit_cols,
+                                                                            d, bits, sv_dev);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int pbl_sobol_scramble(const uint8_t* ltm_bits_dev, const uint8_t* shift_bits_dev, int32_t d, int32_t bits,
+                       uint64_t* sv_dev, uint64_t* shift_dev, void* stream) {
+  if (d < 1 || bits < 1 || bits > 64 || !ltm_bits_dev || !shift_bits_dev || !sv_dev || !shift_dev)
+    return kBadShape;
+  // block = one dimension's `bits` columns (<= 64 threads): the in-place update is block-local
+  pbl::sobol_scramble_kernel<<<d, bits, 0, (cudaStream_t)stream>>>(ltm_bits_dev, shift_bits_dev, d, bits,
+                                                                 sv_dev, shift_dev);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int pbl_sobol_f64(const uint64_t* sv_dev, const uint64_t* shift_dev, int32_t d, int32_t bits,
+                  uint64_t skip, int64_t n, double* out_dev, int64_t row_stride, int64_t col_stride,
+                  void* stream) {
+  if (d < 0 || n < 0 || bits < 1 || bits > 64 || !sv_dev || !shift_dev || !out_dev) return kBadShape;
+  if (n == 0 || d == 0) return kOk;
+  const uint64_t npairs = ((skip + (uint64_t)n + 1) >> 1) - (skip >> 1);
+  dim3 grid((unsigned)((npairs + 255) / 256), (unsigned)d);
+  pbl::sobol_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sv_dev, shift_dev, bits, skip, n, out_dev,
+                                                                 row_stride, col_stride);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int pbl_halton_f64(const int32_t* bases_dev, const int64_t* perms_dev, const int64_t* perm_off_dev,
+                   const int32_t* perm_count_dev, int32_t d, uint64_t start_index, int64_t n,
+                   double* out_dev, int64_t row_stride, int64_t col_stride, void* stream) {
+  if (d < 0 || n < 0 || !bases_dev || !out_dev) return kBadShape;
+  if (n == 0 || d == 0) return kOk;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)d);
+  pbl::halton_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bases_dev, perms_dev, perm_off_dev, perm_count_dev,
+                                                           start_index, n, out_dev, row_stride, col_stride);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+int pbl_lhs_f64(uint64_t seed, int64_t n, int32_t d, int32_t scramble, double* out_dev, int64_t row_stride,
+                int64_t col_stride, void* stream) {
+  if (d < 0 || n < 0 || !out_dev) return kBadShape;
+  if (n == 0 || d == 0) return kOk;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)d);
+  pbl::lhs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, n, scramble, out_dev, row_stride, col_stride);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // extern "C"
