@@ -25,9 +25,10 @@ def test_sobol_bit_exact(d, bits, scramble, seed):
         np.testing.assert_array_equal(mine._shift, ref._shift.astype(np.uint64))
         for n in (1, 70, 1025, 3):  # odd block boundaries exercise the half-used row pairs
             np.testing.assert_array_equal(mine.random(n), ref.random(n))
-        ref.fast_forward(1000)
-        mine.fast_forward(1000)
-        np.testing.assert_array_equal(mine.random(64), ref.random(64))
+        if bits <= 32:  # scipy's own fast_forward rejects 64-bit engines (dtype mismatch in _sobol.pyx)
+            ref.fast_forward(1000)
+            mine.fast_forward(1000)
+            np.testing.assert_array_equal(mine.random(64), ref.random(64))
 
 
 def test_sobol_generator_argument_spawns_like_scipy():
