@@ -80,6 +80,13 @@ PBL_API int pbl_ic_plan_run(pbl_ic_plan* plan, const double* X_dev, int64_t x_ro
                     int64_t x_col_stride, double* Y_dev, int64_t y_row_stride,
                     int64_t y_col_stride, void* stream);
 
+/* Cholesky().set_target(C)(X), reference correlation.py:205-285, on device-resident X -> Y with a
+ * plan whose target has been set (a PBL_IC_ROWS_ONLY plan is enough: no sorts).  Synchronous.
+ * PBL_NOT_POSITIVE_DEFINITE = numpy.linalg.LinAlgError from cholesky(cov) (:271). */
+PBL_API int pbl_cholesky_plan_run(pbl_ic_plan* plan, const double* X_dev, int64_t x_row_stride,
+                                  int64_t x_col_stride, double* Y_dev, int64_t y_row_stride,
+                                  int64_t y_col_stride, void* stream);
+
 /* Same call with HOST buffers (what a NumPy caller holds): copies X to the device, runs, copies Y
  * back.  X and Y must each be one contiguous block in C or F order. */
 PBL_API int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t x_row_stride,
@@ -143,6 +150,66 @@ PBL_API int pbl_halton_f64(const int32_t* bases_dev, const int64_t* perms_dev, c
  * (perm + 1 - U) / n with a counter-based per-column permutation (statistical parity). */
 PBL_API int pbl_lhs_f64(uint64_t seed, int64_t n, int32_t d, int32_t scramble, double* out_dev,
                         int64_t row_stride, int64_t col_stride, void* stream);
+
+/* ---- fused modeling-graph evaluation: the per-node loop of Node.sample_from_quantiles,
+ * src/probabilit/modeling.py:586-612, with Distribution._sample (:795-812, scipy.stats ppf),
+ * Constant._sample (:760-763) and Transform._sample (:954-956, :1007-1009, :1071-1072) fused into
+ * ONE pass per sample: every node value lives in an on-chip slot, only retained nodes are written.
+ *
+ * A program is a list of pbl_graph_instr executed per sample (row).  Operands src[i] >= 0 name a
+ * slot, src[i] < 0 means "use imm[i]" (a scalar parameter / folded Constant).  Values are fp64;
+ * booleans are 0.0 / 1.0 (the host mirror keeps NumPy's result dtype and converts on download).
+ *   PBL_OP_LOAD   dst <- inputs[src[0]][row]      (a quantile column, or a correlated sample column)
+ *   PBL_OP_STORE  outputs[src[1]][row] <- slot src[0]                      (node.samples_ retained)
+ *   PBL_OP_CHECK  if slot src[0] is not finite: report node tag src[1]      (modeling.py:600-606)
+ *   PBL_OP_UNIFORM dst <- Philox uniform of (seed = imm[0] bits, global row = row0 + row, column src[0])
+ *                 -- the same stream as pbl_uniform_f64, generated in-kernel (no quantile read)
+ *   PBL_PPF_*     dst <- scipy.stats.<distr>(shape..., loc, scale).ppf(q) with q = operand 0;
+ *                 operands: NORM(q, loc, scale) UNIFORM_(q, loc, scale) EXPON(q, loc, scale)
+ *                 TRIANG(q, c, loc, scale) GAMMA(q, a, loc, scale) LOGNORM(q, s, loc, scale)
+ *                 POISSON(q, mu, loc) BINOM(q, n, p, loc) BERNOULLI(q, p, loc)
+ *                 including SciPy's wrapper semantics (invalid parameters -> nan, q == 0 / 1 ->
+ *                 support bounds; scipy/stats/_distn_infrastructure.py:2305-2348, :3745-3792)
+ *   arithmetic    the NumPy ufunc behind each Transform class (modeling.py:962-1169). */
+typedef enum pbl_graph_op {
+  PBL_OP_NOP = 0, PBL_OP_LOAD = 1, PBL_OP_STORE = 2, PBL_OP_CHECK = 3, PBL_OP_MOV = 4, PBL_OP_UNIFORM = 5,
+  /* ppf */
+  PBL_PPF_NORM = 16, PBL_PPF_UNIFORM = 17, PBL_PPF_EXPON = 18, PBL_PPF_TRIANG = 19, PBL_PPF_GAMMA = 20,
+  PBL_PPF_LOGNORM = 21, PBL_PPF_POISSON = 22, PBL_PPF_BINOM = 23, PBL_PPF_BERNOULLI = 24,
+  /* binary (dst <- op(a, b)) */
+  PBL_OP_ADD = 32, PBL_OP_MUL = 33, PBL_OP_SUB = 34, PBL_OP_DIV = 35, PBL_OP_POW = 36, PBL_OP_FLOORDIV = 37,
+  PBL_OP_MOD = 38, PBL_OP_MAX = 39, PBL_OP_MIN = 40, PBL_OP_ATAN2 = 41, PBL_OP_LT = 42, PBL_OP_LE = 43,
+  PBL_OP_GT = 44, PBL_OP_GE = 45, PBL_OP_EQ = 46, PBL_OP_NE = 47, PBL_OP_AND = 48, PBL_OP_OR = 49,
+  PBL_OP_ISCLOSE = 50,
+  /* unary (dst <- op(a)) */
+  PBL_OP_NEG = 64, PBL_OP_ABS = 65, PBL_OP_LOG = 66, PBL_OP_EXP = 67, PBL_OP_FLOOR = 68, PBL_OP_CEIL = 69,
+  PBL_OP_SIGN = 70, PBL_OP_SQRT = 71, PBL_OP_SQUARE = 72, PBL_OP_LOG10 = 73, PBL_OP_SIN = 74, PBL_OP_COS = 75,
+  PBL_OP_TAN = 76, PBL_OP_ASIN = 77, PBL_OP_ACOS = 78, PBL_OP_ATAN = 79, PBL_OP_SINH = 80, PBL_OP_COSH = 81,
+  PBL_OP_TANH = 82, PBL_OP_ASINH = 83, PBL_OP_ACOSH = 84, PBL_OP_ATANH = 85, PBL_OP_NOT = 86
+} pbl_graph_op;
+
+typedef struct pbl_graph_instr {
+  int32_t op;     /* pbl_graph_op */
+  int32_t dst;    /* destination slot */
+  int32_t src[4]; /* slot index, or < 0: imm[i] */
+  double imm[4];
+} pbl_graph_instr;
+
+#define PBL_GRAPH_MAX_SLOTS 96
+#define PBL_GRAPH_MAX_INSTR 4096
+
+/* Evaluate `program` for rows 0..n-1.  inputs_dev / outputs_dev are HOST arrays of device column
+ * pointers (contiguous fp64 columns of n rows).  *first_nonfinite receives the smallest node tag
+ * whose CHECK failed, or -1.  row0 = global index of row 0 (for PBL_OP_UNIFORM on a row shard).
+ * Synchronous (returns after the stream has drained). */
+PBL_API int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t n_slots, int64_t n,
+                               uint64_t row0, const double* const* inputs_dev, int32_t n_inputs,
+                               double* const* outputs_dev, int32_t n_outputs, int32_t* first_nonfinite,
+                               void* stream);
+/* The same special functions one element at a time, for the parity tests:
+ * what = a PBL_PPF_* code; p0..p2 = the distribution's operands after q (see above). */
+PBL_API int pbl_ppf_f64(int32_t what, const double* q_dev, int64_t n, double p0, double p1, double p2,
+                        double* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

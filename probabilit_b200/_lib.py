@@ -44,6 +44,7 @@ SIGNATURES = {
     "pbl_ic_plan_bytes": (_u64, [_vp]),
     "pbl_ic_plan_set_target": (C.c_int, [_vp, _pd]),
     "pbl_ic_plan_run": (C.c_int, [_vp, _pd, _i64, _i64, _pd, _i64, _i64, _vp]),
+    "pbl_cholesky_plan_run": (C.c_int, [_vp, _pd, _i64, _i64, _pd, _i64, _i64, _vp]),
     "pbl_iman_conover_f64": (C.c_int, [_pd, _i64, _i32, _i64, _i64, _pd, _pd, _i64, _i64]),
     "pbl_ic_stage_begin": (C.c_int, [_vp, _vp]),
     "pbl_ic_stage_rank_scores": (C.c_int, [_vp, _pd, _i64, _i64, _i32, _i32, _vp]),
@@ -59,7 +60,14 @@ SIGNATURES = {
     "pbl_sobol_f64": (C.c_int, [_vp, _vp, _i32, _i32, _u64, _i64, _pd, _i64, _i64, _vp]),
     "pbl_halton_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _u64, _i64, _pd, _i64, _i64, _vp]),
     "pbl_lhs_f64": (C.c_int, [_u64, _i64, _i32, _i32, _pd, _i64, _i64, _vp]),
+    "pbl_graph_eval_f64": (C.c_int, [_vp, _i32, _i32, _i64, _u64, _vp, _i32, _vp, _i32, C.POINTER(_i32), _vp]),
+    "pbl_ppf_f64": (C.c_int, [_i32, _pd, _i64, C.c_double, C.c_double, C.c_double, _pd, _vp]),
 }
+
+
+class GraphInstr(C.Structure):
+    """pbl_graph_instr of include/probabilit_b200.h"""
+    _fields_ = [("op", _i32), ("dst", _i32), ("src", _i32 * 4), ("imm", C.c_double * 4)]
 
 
 def load():

@@ -24,6 +24,54 @@ class CorrelatorError(Exception):
     pass
 
 
+def nearest_correlation_matrix(matrix, *, weights=None, eps=1e-6, verbose=False):
+    """Correlation matrix nearest to ``matrix`` in the Frobenius norm, with smallest eigenvalue
+    >= 10 * eps / K -- the problem the reference hands to cvxpy/SCS (correlation.py:59-150).
+
+    Not on the hot path (one K x K problem per ``sample`` call; SURVEY.md section 8 keeps it on the
+    host): solved here with Higham's alternating projections + Dykstra's correction (N. Higham,
+    "Computing the nearest correlation matrix", 2002) in NumPy, so that ``.correlate()`` graphs
+    work without cvxpy.  A matrix that is already feasible is returned unchanged (SCS returns it
+    to ~1e-6).  Elementwise ``weights`` other than all-ones are not supported."""
+    if not isinstance(matrix, np.ndarray):
+        raise TypeError("Input argument `matrix` must be np.ndarray.")
+    if not (matrix.ndim == 2 and matrix.shape[0] == matrix.shape[1]):
+        raise ValueError("Input argument `matrix` must be square.")
+    if weights is not None:
+        if not isinstance(weights, np.ndarray):
+            raise TypeError("Input argument `weights` must be np.ndarray.")
+        if weights.shape != matrix.shape:
+            raise ValueError("Argument `weights` must have same shape as `matrix`.")
+        if not np.allclose(weights, weights.flat[0]):
+            raise NotImplementedError("elementwise weights need the reference's cvxpy/SCS solver")
+    K = matrix.shape[0]
+    floor = 10.0 * eps / K
+    G = np.array(matrix, dtype=float)
+    sym = 0.5 * (G + G.T)
+    if np.allclose(G, G.T) and np.allclose(np.diag(G), 1.0) and np.linalg.eigvalsh(sym).min() >= floor:
+        return G
+    Y, dS = sym.copy(), np.zeros_like(sym)
+    for it in range(10000):
+        R = Y - dS
+        w, V = np.linalg.eigh(R)
+        X = (V * np.maximum(w, floor)) @ V.T  # projection on {X : X - floor*I >= 0}
+        dS = X - R
+        Y_new = X.copy()
+        np.fill_diagonal(Y_new, 1.0)  # projection on the unit diagonal
+        done = np.linalg.norm(Y_new - Y, "fro") <= 1e-3 * eps * max(1.0, np.linalg.norm(Y_new, "fro"))
+        Y = Y_new
+        if verbose:
+            print(f"nearest_correlation_matrix: iteration {it}, min eig {np.linalg.eigvalsh(Y).min():.3e}")
+        if done:
+            break
+    # finish on the PSD side with an exact unit diagonal: shrink towards the identity if needed
+    lam = np.linalg.eigvalsh(Y).min()
+    if lam < floor:
+        t = (floor - lam) / (1.0 - lam)
+        Y = (1.0 - t) * Y + t * np.eye(K)
+    return 0.5 * (Y + Y.T)
+
+
 def _is_positive_definite(X):
     try:
         np.linalg.cholesky(X)
@@ -137,12 +185,12 @@ def _raise_for_status(st):
     raise ValueError(_lib.last_error())
 
 
-class ImanConover(Correlator):
-    """Iman-Conover transform on the GPU (reference correlation.py:288-425).
+class _PlanCorrelator(Correlator):
+    """Shared plumbing of the correlators that run on a pbl_ic_plan: workspace reuse, host and
+    device entry points, status -> exception mapping."""
 
-    >>> transform = ImanConover().set_target(np.array([[1, 0.7], [0.7, 1]]))   # doctest: +SKIP
-    >>> X_transformed = transform(X)                                           # doctest: +SKIP
-    """
+    _entry = None        # C symbol that runs the transform on a plan
+    _rows_only = False   # plan without sort workspace
 
     def __init__(self, device=None, col_batch=0):
         self.device = device
@@ -161,7 +209,7 @@ class ImanConover(Correlator):
             if p is not None:
                 p.close()
             self._free_dev_bufs()
-            p = self._plan = _IcPlan(n, k, device, self.col_batch)
+            p = self._plan = _IcPlan(n, k, device, self.col_batch, rows_only=self._rows_only)
         p.set_target(self.P)
         return p
 
@@ -185,10 +233,18 @@ class ImanConover(Correlator):
         except Exception:
             pass
 
+    def _raise(self, st):
+        _raise_for_status(st)
+
+    def _run(self, plan, x_ptr, xrs, xcs, y_ptr, yrs, ycs, stream):
+        fn = getattr(plan.lib, self._entry)
+        st = _lib.check(fn(plan.handle, C.c_void_p(x_ptr), xrs, xcs, C.c_void_p(y_ptr), yrs, ycs, stream), self._entry)
+        self._raise(st)
+
     # ------------------------------------------------------------------ the transform
     def __call__(self, X, *, out=None):
         """Transform an input matrix X of shape (N, K); same contract as the reference's
-        ``ImanConover.__call__`` (correlation.py:368-425).
+        ``__call__`` (correlation.py:248-285 / :368-425).
 
         ``out`` (extension, optional): a float64 array with X's shape and memory order to
         receive the result (e.g. page-locked memory, so that the device-to-host copy runs at
@@ -223,28 +279,71 @@ class ImanConover(Correlator):
         rs, cs = _strides_elems(Xd.shape, Xd.strides, 8)
         yrs, ycs = _strides_elems(result.shape, result.strides, 8)
         _lib.check(lib.pbl_memcpy_h2d(dX, Xd.ctypes.data, nbytes, None), "pbl_memcpy_h2d")
-        st = _lib.check(lib.pbl_ic_plan_run(plan.handle, dX, rs, cs, dY, yrs, ycs, None), "pbl_ic_plan_run")
-        _raise_for_status(st)
+        self._run(plan, dX, rs, cs, dY, yrs, ycs, None)
         _lib.check(lib.pbl_memcpy_d2h(result.ctypes.data, dY, nbytes, None), "pbl_memcpy_d2h")
         _lib.check(lib.pbl_stream_synchronize(None), "pbl_stream_synchronize")
-        if result.dtype != X.dtype:
+        if result.dtype != X.dtype and self._keeps_dtype:
             result = result.astype(X.dtype)  # np.empty_like(X) keeps X's dtype in the reference
         return result
 
     def _call_device(self, X, N, K):
         import torch
 
-        lib = _lib.require_gpu()
+        _lib.require_gpu()
         if X.dtype != torch.float64:
             raise TypeError("device-resident X must be float64")
         device = X.device.index if X.device.index is not None else torch.cuda.current_device()
         plan = self._get_plan(N, K, device)
         Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
         stream = torch.cuda.current_stream(X.device).cuda_stream
-        st = _lib.check(
-            lib.pbl_ic_plan_run(plan.handle, X.data_ptr(), X.stride(0), X.stride(1), Y.data_ptr(),
-                                Y.stride(0), Y.stride(1), C.c_void_p(stream)),
-            "pbl_ic_plan_run",
-        )
-        _raise_for_status(st)
+        self._run(plan, X.data_ptr(), X.stride(0), X.stride(1), Y.data_ptr(), Y.stride(0), Y.stride(1),
+                  C.c_void_p(stream))
         return Y
+
+    def correlate_device(self, X):
+        """(n, k) ``DeviceColumns`` -> new ``DeviceColumns`` (no host traffic): the graph path's
+        ``correlator_instance(samples_input)`` (reference modeling.py:580-581) on device columns."""
+        from ._device import DeviceColumns
+
+        if not (hasattr(self, "C") and hasattr(self, "P")):
+            raise CorrelatorError("User must call `set_target` first.")
+        N, K = X.n, X.k
+        if self.P.shape[0] != K:
+            raise ValueError(f"Shape of `X` ({(N, K)}) does not match shape of correlation matrix ({self.P.shape})")
+        if N <= K:
+            raise ValueError(f"The matrix X must have rows > columns. Got shape: {(N, K)}")
+        device = 0 if self.device is None else int(self.device)
+        plan = self._get_plan(N, K, device)
+        Y = DeviceColumns(N, K)
+        self._run(plan, X.ptr, 1, N, Y.ptr, 1, N, None)
+        return Y
+
+
+class ImanConover(_PlanCorrelator):
+    """Iman-Conover transform on the GPU (reference correlation.py:288-425).
+
+    >>> transform = ImanConover().set_target(np.array([[1, 0.7], [0.7, 1]]))   # doctest: +SKIP
+    >>> X_transformed = transform(X)                                           # doctest: +SKIP
+    """
+
+    _entry = "pbl_ic_plan_run"
+    _keeps_dtype = True
+
+
+class Cholesky(_PlanCorrelator):
+    """Cholesky transform on the GPU (reference correlation.py:205-285): standardise, remove the
+    sample correlation with its Cholesky factor, impose the target's, restore mean and scale.
+    Does not preserve the marginals.
+
+    >>> transform = Cholesky().set_target(np.array([[1, 0.7], [0.7, 1]]))      # doctest: +SKIP
+    >>> X_transformed = transform(X)                                           # doctest: +SKIP
+    """
+
+    _entry = "pbl_cholesky_plan_run"
+    _rows_only = True
+    _keeps_dtype = False  # `mean + X_n @ ...` is float64 whatever X was
+
+    def _raise(self, st):
+        if st == _lib.STATUS_NOT_PD:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")  # np.linalg.cholesky(cov), :271
+        _raise_for_status(st)

@@ -118,6 +118,12 @@ int pbl_ic_plan_run(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs
   return pbl::ic_plan_run(plan->impl, X, xrs, xcs, Y, yrs, ycs, (cudaStream_t)stream);
 }
 
+int pbl_cholesky_plan_run(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, double* Y,
+                          int64_t yrs, int64_t ycs, void* stream) {
+  if (!plan || !X || !Y) return kBadShape;
+  return pbl::cholesky_correlator_run(plan->impl, X, xrs, xcs, Y, yrs, ycs, (cudaStream_t)stream);
+}
+
 static bool contiguous_layout(int64_t n, int32_t k, int64_t rs, int64_t cs) {
   return (rs == 1 && cs == n) || (cs == 1 && rs == k) || (n == 1 && cs == 1) || (k == 1 && rs == 1);
 }

@@ -431,27 +431,33 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nrb,
 // T = Q^-T P^T (upper triangular).  numpy cov/corrcoef + np.linalg.cholesky +
 // solve_triangular(...) @ P.T of correlation.py:398-414, for the k x k part.
 // ======================================================================================
+// MODE 0 (Iman-Conover): W = corrcoef.   MODE 1 (Cholesky correlator, correlation.py:263-285):
+// W = np.cov(X_n, ddof=0) of the standardised data, and the finished T is scaled by the column
+// standard deviations (`transform * std`, :285).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsum,
                   const double* __restrict__ P, double* __restrict__ W, double* __restrict__ T,
-                  int k, double n_total, uint32_t* __restrict__ flags) {
+                  int k, double n_total, uint32_t* __restrict__ flags, const double* __restrict__ colstd) {
   const int tid = threadIdx.x, nth = blockDim.x;
-  const double inv = 1.0 / (n_total - 1.0);
+  const double inv = 1.0 / (MODE == 0 ? n_total - 1.0 : n_total);
   for (int e = tid; e < k * k; e += nth) {
     int i = e / k, j = e % k;
     W[e] = (G[e] - colsum[i] * colsum[j] / n_total) * inv;
   }
   __syncthreads();
-  for (int i = tid; i < k; i += nth) T[i] = sqrt(W[(size_t)i * k + i]);
-  __syncthreads();
-  for (int e = tid; e < k * k; e += nth) {
-    int i = e / k, j = e % k;
-    double c = W[e] / T[i];
-    c = c / T[j];
-    W[e] = fmin(fmax(c, -1.0), 1.0);  // NaN stays NaN only if both are NaN: checked below
-    if (c != c) W[e] = c;
+  if (MODE == 0) {
+    for (int i = tid; i < k; i += nth) T[i] = sqrt(W[(size_t)i * k + i]);
+    __syncthreads();
+    for (int e = tid; e < k * k; e += nth) {
+      int i = e / k, j = e % k;
+      double c = W[e] / T[i];
+      c = c / T[j];
+      W[e] = fmin(fmax(c, -1.0), 1.0);  // NaN stays NaN only if both are NaN: checked below
+      if (c != c) W[e] = c;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // right-looking Cholesky, lower triangle
   for (int j = 0; j < k; ++j) {
     double d = W[(size_t)j * k + j];
@@ -487,7 +493,70 @@ chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsu
       for (int m = i + 1; m <= c; ++m) s -= W[(size_t)m * k + i] * T[(size_t)m * k + c];
       T[(size_t)i * k + c] = s / W[(size_t)i * k + i];
     }
+    if (MODE == 1) {
+      const double sd = colstd[c];
+      for (int i = 0; i <= c; ++i) T[(size_t)i * k + c] *= sd;
+    }
   }
+}
+
+// ======================================================================================
+// Cholesky correlator helpers (reference correlation.py:205-285): column mean / standard
+// deviation (two passes, fixed-order reductions), standardisation, and the final `mean + ...`.
+// ======================================================================================
+constexpr int kMomBlocks = 256;  // partial sums per column
+
+// MODE 0: sum x      MODE 1: sum (x - mean)^2
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_moment_kernel(const double* __restrict__ X, int64_t row_stride, int64_t col_stride, int64_t n,
+                  const double* __restrict__ mean, double* __restrict__ partials) {
+  __shared__ double red[256];
+  const int col = blockIdx.y;
+  const double* xc = X + (int64_t)col * col_stride;
+  const double m = MODE == 1 ? mean[col] : 0.0;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+  double acc = 0.0;
+  for (int64_t r = lo + threadIdx.x; r < hi; r += 256) {
+    const double v = ld_stream_f64(xc + r * row_stride);
+    acc += MODE == 1 ? (v - m) * (v - m) : v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[(size_t)col * gridDim.x + blockIdx.x] = red[0];
+}
+
+template <int MODE>
+__global__ void col_moment_finish_kernel(const double* __restrict__ partials, int nb, int k, double n,
+                                         double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s += partials[(size_t)c * nb + b];
+  out[c] = MODE == 1 ? sqrt(s / n) : s / n;
+}
+
+__global__ void __launch_bounds__(256)
+standardise_kernel(const double* __restrict__ X, int64_t row_stride, int64_t col_stride, int64_t n,
+                   const double* __restrict__ mean, const double* __restrict__ sd, double* __restrict__ S) {
+  const int col = blockIdx.y;
+  const double m = mean[col], d = sd[col];
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
+    S[(int64_t)col * n + r] = (ld_stream_f64(X + (int64_t)col * col_stride + r * row_stride) - m) / d;
+}
+
+__global__ void __launch_bounds__(256)
+add_mean_kernel(const double* __restrict__ S, int64_t n, const double* __restrict__ mean,
+                double* __restrict__ Y, int64_t row_stride, int64_t col_stride) {
+  const int col = blockIdx.y;
+  const double m = mean[col];
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
+    Y[(int64_t)col * col_stride + r * row_stride] = m + ld_stream_f64(S + (int64_t)col * n + r);
 }
 
 // ======================================================================================
@@ -686,6 +755,7 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->T);
   cudaFree(p->P);
   cudaFree(p->gram_partials);
+  cudaFree(p->moments);
   delete p;
 }
 
@@ -773,8 +843,8 @@ int ic_stage_solve(IcPlan* p, int64_t n_total, cudaStream_t stream) {
     set_last_error("ic: set_target has not been called");
     return kBadShape;
   }
-  chol_solve_kernel<<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, p->k,
-                                          (double)n_total, p->flags);
+  chol_solve_kernel<0><<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, p->k,
+                                             (double)n_total, p->flags, nullptr);
   PBL_LAUNCH_CHECK();
   return kOk;
 }
@@ -814,6 +884,54 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
                                  col_stride, p->use_lookback, stream));
+  }
+  return kOk;
+}
+
+// Cholesky().set_target(C)(X) (reference correlation.py:248-285) on device-resident data:
+//   mean / std (ddof 0) per column, X_n = (X - mean) / std, cov = np.cov(X_n, ddof=0),
+//   T = chol(cov)^-T P^T scaled by std per column, Y = mean + X_n @ T.
+// Works on any plan (rows-only is enough: no sorts).
+int cholesky_correlator_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, double* Y, int64_t yrs,
+                            int64_t ycs, cudaStream_t stream) {
+  if (!p->has_target) {
+    set_last_error("User must call `set_target` first.");
+    return kBadShape;
+  }
+  const int k = p->k;
+  const int64_t n = p->n;
+  if (!p->moments) {
+    PBL_CUDA_CHECK(cudaMalloc((void**)&p->moments, ((size_t)2 * k + (size_t)k * kMomBlocks) * 8));
+    p->bytes += ((size_t)2 * k + (size_t)k * kMomBlocks) * 8;
+  }
+  double* mean = p->moments;
+  double* sd = p->moments + k;
+  double* partials = p->moments + 2 * k;
+  PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
+  const dim3 mg(kMomBlocks, k);
+  col_moment_kernel<0><<<mg, 256, 0, stream>>>(X, xrs, xcs, n, nullptr, partials);
+  PBL_LAUNCH_CHECK();
+  col_moment_finish_kernel<0><<<(k + 127) / 128, 128, 0, stream>>>(partials, kMomBlocks, k, (double)n, mean);
+  PBL_LAUNCH_CHECK();
+  col_moment_kernel<1><<<mg, 256, 0, stream>>>(X, xrs, xcs, n, mean, partials);
+  PBL_LAUNCH_CHECK();
+  col_moment_finish_kernel<1><<<(k + 127) / 128, 128, 0, stream>>>(partials, kMomBlocks, k, (double)n, sd);
+  PBL_LAUNCH_CHECK();
+  const unsigned rb = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
+  standardise_kernel<<<dim3(rb, k), 256, 0, stream>>>(X, xrs, xcs, n, mean, sd, p->scores);
+  PBL_LAUNCH_CHECK();
+  PBL_RETURN_IF(ic_stage_gram(p, stream));
+  chol_solve_kernel<1><<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, k, (double)n, p->flags, sd);
+  PBL_LAUNCH_CHECK();
+  PBL_RETURN_IF(ic_stage_transform(p, stream));
+  add_mean_kernel<<<dim3(rb, k), 256, 0, stream>>>(p->scores, n, mean, Y, yrs, ycs);
+  PBL_LAUNCH_CHECK();
+  uint32_t h[8];
+  PBL_CUDA_CHECK(cudaMemcpyAsync(h, p->flags, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  PBL_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (h[kFlagNotPD]) {
+    set_last_error("Matrix is not positive definite");
+    return kNotPositiveDefinite;
   }
   return kOk;
 }

@@ -29,6 +29,7 @@ struct IcPlan {
   double* work = nullptr;      // [k][k] scratch: R, then Q (lower Cholesky factor)
   double* T = nullptr;         // [k][k] row-major, upper triangular: correlated = scores @ T
   double* P = nullptr;         // [k][k] row-major lower Cholesky factor of the target C
+  double* moments = nullptr;   // Cholesky correlator: [k] mean, [k] std, [k][256] partial sums (lazy)
   uint32_t* flags = nullptr;   // [8], see SortFlag in sort.cuh
   size_t bytes = 0;            // device bytes held by the plan
 };
@@ -54,5 +55,9 @@ int ic_stage_transform(IcPlan* plan, cudaStream_t stream);
 int ic_stage_rank_gather(IcPlan* plan, double* Y, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream);
 int ic_read_status(IcPlan* plan, cudaStream_t stream);
+
+// Cholesky correlator (reference correlation.py:205-285); synchronous like ic_plan_run.
+int cholesky_correlator_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
+                            double* Y, int64_t y_row_stride, int64_t y_col_stride, cudaStream_t stream);
 
 }  // namespace pbl

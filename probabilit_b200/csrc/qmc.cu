@@ -9,35 +9,10 @@
 // communication (skip-ahead = start the index at the shard's first row).
 #include "../../include/probabilit_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace pbl {
 namespace {
-
-// ------------------------------------------------------------------------------ Philox4x32-10
-struct U4 {
-  uint32_t x, y, z, w;
-};
-__device__ __forceinline__ U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    U4 n;
-    n.x = hi1 ^ ctr.y ^ k0;
-    n.y = lo1;
-    n.z = hi0 ^ ctr.w ^ k1;
-    n.w = lo0;
-    ctr = n;
-    k0 += W0;
-    k1 += W1;
-  }
-  return ctr;
-}
-// 53-bit uniform in [0, 1) from two 32-bit words (the construction NumPy uses for its doubles)
-__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
-  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
-}
 
 // one thread: rows (2t, 2t+1) of one column
 __global__ void __launch_bounds__(256)

@@ -1,0 +1,351 @@
+// Device special functions behind the inverse CDFs of the graph kernel (graph.cu).
+//
+// The reference evaluates  getattr(scipy.stats, distr)(*args, **kwargs).ppf(q)
+// (src/probabilit/modeling.py:795-812).  SciPy 1.18's sources for the special functions are not
+// on the box (compiled xsf / cdflib / Boost), so these are restatements of the *published*
+// algorithms SciPy uses, evaluated in the same operation order where that matters:
+//   gamma.ppf   -> gammaincinv(a, q): Cephes/xsf `igami`/`igamci` = an initial guess followed by
+//                  Halley steps on P(a, x) - p  (DiDonato & Morris 1986 starting values);
+//                  P, Q: Cephes `igam`/`igamc` (power series DLMF 8.11.4, series DLMF 8.7.3,
+//                  continued fraction DLMF 8.9.2) with the Boost Lanczos(13, g=6.0247) prefactor.
+//   poisson.ppf -> min{k : pdtr(k, mu) >= q}   (scipy/stats/_discrete_distns.py:1015-1019)
+//   binom.ppf   -> min{k : cdf(k; n, p) >= q}  (Boost quantile, _discrete_distns.py:100-101)
+// Accuracy contract (tests/test_graph_gpu.py): poisson/binom are exact integers; gamma is
+// reported as a ulp distribution against scipy (scipy itself is up to 18 ulp from the truth).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "ndtri.cuh"
+
+namespace pbl {
+
+constexpr double kMachEp = 1.11022302462515654042E-16;
+constexpr double kMaxLog = 7.09782712893383996843E2;
+constexpr double kInf = __builtin_huge_val();
+#define PBL_NAN __longlong_as_double(0x7FF8000000000000LL)
+
+// Lanczos sum (N = 13, g = 6.024680040776729583740234375), exp(g)-scaled: Boost lanczos13m53,
+// the form SciPy's igam_fac uses.  Rational function evaluated in x (|x| <= 1) or 1/x.
+__device__ __noinline__ double lanczos_sum_expg_scaled(double x) {
+  const double num[13] = {0.006061842346248906525783753964555936883222,
+                          0.5098416655656676188125178644804694509993,
+                          19.51992788247617482847860966235652136208,
+                          449.9445569063168119446858607650988409623,
+                          6955.999602515376140356310115515198987526,
+                          75999.29304014542649875303443598909137092,
+                          601859.6171681098786670226533699352302507,
+                          3481712.15498064590882071018964774556468,
+                          14605578.08768506808414169982791359218571,
+                          43338889.32467613834773723740590533316085,
+                          86363131.28813859145546927288977868422342,
+                          103794043.1163445451906271053616070238554,
+                          56906521.91347156388090791033559122686859};
+  const double den[13] = {1., 66., 1925., 32670., 357423., 2637558., 13339535., 45995730.,
+                          105258076., 150917976., 120543840., 39916800., 0.};
+  double na, da;
+  if (fabs(x) > 1.0) {
+    const double y = 1.0 / x;
+    na = num[12];
+    da = den[12];
+#pragma unroll
+    for (int i = 11; i >= 0; --i) {
+      na = na * y + num[i];
+      da = da * y + den[i];
+    }
+  } else {
+    na = num[0];
+    da = den[0];
+#pragma unroll
+    for (int i = 1; i < 13; ++i) {
+      na = na * x + num[i];
+      da = da * x + den[i];
+    }
+  }
+  return na / da;
+}
+
+// x^a e^-x / Gamma(a)
+__device__ __noinline__ double igam_fac(double a, double x) {
+  const double g = 6.024680040776729583740234375;
+  if (fabs(a - x) > 0.4 * fabs(a)) {
+    const double ax = a * log(x) - x - lgamma(a);
+    if (ax < -kMaxLog) return 0.0;
+    return exp(ax);
+  }
+  const double fac = a + g - 0.5;
+  double res = sqrt(fac / 2.718281828459045) / lanczos_sum_expg_scaled(a);
+  if (a < 200.0 && x < 200.0) {
+    res *= exp(a - x) * pow(x / fac, a);
+  } else {
+    const double num = x - a - g + 0.5;
+    const double numfac = num / fac;
+    res *= exp(a * (log1p(numfac) - numfac) + x * (0.5 - g) / fac);
+  }
+  return res;
+}
+
+// P(a, x) by the power series x^a e^-x / Gamma(a+1) * sum_n x^n / ((a+1)...(a+n))
+__device__ __noinline__ double igam_series(double a, double x) {
+  const double ax = igam_fac(a, x);
+  if (ax == 0.0) return 0.0;
+  double r = a, c = 1.0, ans = 1.0;
+  for (int i = 0; i < 4000; ++i) {
+    r += 1.0;
+    c *= x / r;
+    ans += c;
+    if (c <= kMachEp * ans) break;
+  }
+  return ans * ax / a;
+}
+
+// Q(a, x) for small x without cancellation (DLMF 8.7.3)
+__device__ __noinline__ double igamc_series(double a, double x) {
+  double fac = 1.0, sum = 0.0;
+  for (int n = 1; n < 2000; ++n) {
+    fac *= -x / n;
+    const double term = fac / (a + n);
+    sum += term;
+    if (fabs(term) <= kMachEp * fabs(sum)) break;
+  }
+  const double logx = log(x);
+  const double term = -expm1(a * logx - lgamma(1.0 + a));
+  return term - exp(a * logx - lgamma(a)) * sum;
+}
+
+// Q(a, x) by the continued fraction (DLMF 8.9.2)
+__device__ __noinline__ double igamc_cf(double a, double x) {
+  const double big = 4.503599627370496e15, biginv = 2.22044604925031308085e-16;
+  const double ax = igam_fac(a, x);
+  if (ax == 0.0) return 0.0;
+  double y = 1.0 - a, z = x + y + 1.0, c = 0.0;
+  double pkm2 = 1.0, qkm2 = x, pkm1 = x + 1.0, qkm1 = z * x;
+  double ans = pkm1 / qkm1;
+  for (int i = 0; i < 4000; ++i) {
+    c += 1.0;
+    y += 1.0;
+    z += 2.0;
+    const double yc = y * c;
+    const double pk = pkm1 * z - pkm2 * yc;
+    const double qk = qkm1 * z - qkm2 * yc;
+    double t = 1.0;
+    if (qk != 0.0) {
+      const double r = pk / qk;
+      t = fabs((ans - r) / r);
+      ans = r;
+    }
+    pkm2 = pkm1;
+    pkm1 = pk;
+    qkm2 = qkm1;
+    qkm1 = qk;
+    if (fabs(pk) > big) {
+      pkm2 *= biginv;
+      pkm1 *= biginv;
+      qkm2 *= biginv;
+      qkm1 *= biginv;
+    }
+    if (t <= kMachEp) break;
+  }
+  return ans * ax;
+}
+
+__device__ double igamc(double a, double x);
+
+// regularised lower incomplete gamma P(a, x)
+__device__ __noinline__ double igam(double a, double x) {
+  if (x < 0.0 || a < 0.0 || a != a || x != x) return PBL_NAN;
+  if (a == 0.0) return x > 0.0 ? 1.0 : PBL_NAN;
+  if (x == 0.0) return 0.0;
+  if (isinf(a)) return isinf(x) ? PBL_NAN : 0.0;
+  if (isinf(x)) return 1.0;
+  if (x > 1.0 && x > a) return 1.0 - igamc(a, x);
+  return igam_series(a, x);
+}
+
+// regularised upper incomplete gamma Q(a, x)
+__device__ __noinline__ double igamc(double a, double x) {
+  if (x < 0.0 || a < 0.0 || a != a || x != x) return PBL_NAN;
+  if (a == 0.0) return x > 0.0 ? 0.0 : PBL_NAN;
+  if (x == 0.0) return 1.0;
+  if (isinf(a)) return isinf(x) ? PBL_NAN : 1.0;
+  if (isinf(x)) return 0.0;
+  if (x > 1.1) return (x < a) ? 1.0 - igam_series(a, x) : igamc_cf(a, x);
+  if (x <= 0.5) return (-0.4 / log(x) < a) ? 1.0 - igam_series(a, x) : igamc_series(a, x);
+  return (x * 1.1 < a) ? 1.0 - igam_series(a, x) : igamc_series(a, x);
+}
+
+// Starting value for the inverse of P(a, .) at p (q = 1 - p), after DiDonato & Morris (1986),
+// "Computation of the incomplete gamma function ratios and their inverse" -- eqs. 21-25, 31-33.
+__device__ __noinline__ double igami_start(double a, double p, double q) {
+  const double euler = 0.5772156649015328606;
+  if (a == 1.0) return -log(q);
+  if (a < 1.0) {
+    const double g = tgamma(a);
+    const double b = q * g;
+    if (b > 0.6 || (b >= 0.45 && a >= 0.3)) {
+      const double u = (b * q > 1e-8 && q > 1e-5) ? pow(p * g * a, 1.0 / a) : exp(-q / a - euler);
+      return u / (1.0 - u / (a + 1.0));
+    }
+    if (a < 0.3 && b >= 0.35) {
+      const double t = exp(-euler - b);
+      const double u = t * exp(t);
+      return t * exp(u);
+    }
+    const double y = -log(b);
+    const double u = y - (1.0 - a) * log(y);
+    if (b > 0.15 || a >= 0.3) return y - (1.0 - a) * log(u) - log(1.0 + (1.0 - a) / (1.0 + u));
+    return y - (1.0 - a) * log(u) -
+           log((u * u + 2.0 * (3.0 - a) * u + (2.0 - a) * (3.0 - a)) / (u * u + (5.0 - a) * u + 2.0));
+  }
+  // a > 1: Cornish-Fisher expansion around the normal quantile (eq. 31)
+  const double s = (p < 0.5) ? ndtri(p) : -ndtri(q);
+  const double s2 = s * s, ra = sqrt(a);
+  double w = a + s * ra + (s2 - 1.0) / 3.0;
+  w += (s2 * s - 7.0 * s) / (36.0 * ra);
+  w -= (3.0 * s2 * s2 + 7.0 * s2 - 16.0) / (810.0 * a);
+  w += (9.0 * s2 * s2 * s + 256.0 * s2 * s - 433.0 * s) / (38880.0 * a * ra);
+  if (p > 0.5) {
+    if (w < 3.0 * a) return w;
+    const double lb = log(q) + lgamma(a);
+    const double u = -lb + (a - 1.0) * log(w) - log(1.0 + (1.0 - a) / (1.0 + w));
+    return -lb + (a - 1.0) * log(u) - log(1.0 + (1.0 - a) / (1.0 + u));
+  }
+  if (w < 0.15 * (a + 1.0) || !(w > 0.0)) {
+    // small-x end: P(a, x) ~ x^a e^-x / Gamma(a+1) * (1 + x/(a+1) + ...)   (eq. 35)
+    const double ap1 = a + 1.0, ap2 = a + 2.0;
+    const double v = log(p) + lgamma(ap1);
+    double z = exp((v + (w > 0.0 ? w : 0.0)) / a);
+    double t = log1p(z / ap1 * (1.0 + z / ap2));
+    z = exp((v + z - t) / a);
+    t = log1p(z / ap1 * (1.0 + z / ap2));
+    z = exp((v + z - t) / a);
+    t = log1p(z / ap1 * (1.0 + z / ap2 * (1.0 + z / (a + 3.0))));
+    return exp((v + z - t) / a);
+  }
+  return w;
+}
+
+// scipy.special.gammaincinv(a, p): x with P(a, x) = p.  Halley steps exactly as Cephes/xsf igami
+// (on P for p <= 0.9, on Q for p > 0.9 as igamci), iterated to a fixed point instead of a
+// fixed 3 steps so that the result does not depend on the starting value.
+__device__ __noinline__ double igami(double a, double p) {
+  if (a != a || p != p) return PBL_NAN;
+  if (a < 0.0 || p < 0.0 || p > 1.0) return PBL_NAN;
+  if (p == 0.0) return 0.0;
+  if (p == 1.0) return kInf;
+  if (a == 0.0) return 0.0;
+  const bool upper = p > 0.9;
+  const double q = 1.0 - p;
+  double x = igami_start(a, p, q);
+  if (!(x > 0.0) || isinf(x)) x = a > 1.0 ? a : 0.5;
+  for (int it = 0; it < 12; ++it) {
+    const double fac = igam_fac(a, x);
+    if (fac == 0.0) break;
+    const double f_fp = upper ? (igamc(a, x) - q) * x / (-fac) : (igam(a, x) - p) * x / fac;
+    const double fpp_fp = -1.0 + (a - 1.0) / x;
+    double xn = isinf(fpp_fp) ? x - f_fp : x - f_fp / (1.0 - 0.5 * f_fp * fpp_fp);
+    if (!(xn > 0.0)) xn = 0.5 * x;  // overshoot past the support: bisect towards 0
+    const double dx = fabs(xn - x);
+    x = xn;
+    if (it >= 2 && dx <= 4.0 * kMachEp * x) break;
+    if (isinf(x) || x != x) break;
+  }
+  return x;
+}
+
+// log of the Poisson pmf at integer k
+__device__ __forceinline__ double poisson_logpmf(double k, double mu) {
+  return k * log(mu) - mu - lgamma(k + 1.0);
+}
+
+// poisson(mu)._ppf(q) for 0 < q < 1, mu >= 0:  min{k >= 0 : pdtr(k, mu) >= q}
+__device__ __noinline__ double poisson_ppf_core(double q, double mu) {
+  if (mu == 0.0) return 0.0;
+  if (mu <= 32.0) {
+    double pk = exp(-mu), F = pk, k = 0.0;
+    const double kmax = 400.0;
+    while (F < q && k < kmax) {
+      k += 1.0;
+      pk *= mu / k;
+      F += pk;
+    }
+    return k;
+  }
+  // start at the Cornish-Fisher guess, get the CDF there from Q(k+1, mu), then walk
+  const double z = ndtri(q), sd = sqrt(mu);
+  double k = floor(mu + z * sd + (z * z - 1.0) / 6.0);
+  if (k < 0.0) k = 0.0;
+  double F = igamc(k + 1.0, mu);
+  double pk = exp(poisson_logpmf(k, mu));
+  if (F >= q) {
+    while (k > 0.0) {
+      const double Fm = F - pk;  // cdf(k - 1)
+      if (!(Fm >= q)) break;
+      F = Fm;
+      pk *= k / mu;
+      k -= 1.0;
+    }
+    return k;
+  }
+  const double kmax = mu + 40.0 * sd + 40.0;
+  while (F < q && k < kmax) {
+    k += 1.0;
+    pk *= mu / k;
+    F += pk;
+  }
+  return k;
+}
+
+// binom(n, p)._ppf(q) for 0 < q < 1, integer n >= 0, 0 <= p <= 1:  min{k : cdf(k) >= q}
+__device__ __noinline__ double binom_ppf_core(double q, double n, double p) {
+  if (n == 0.0 || p == 0.0) return 0.0;
+  if (p == 1.0) return n;
+  const double odds = p / (1.0 - p);
+  const double l0 = n * log1p(-p);  // log pmf(0)
+  if (l0 > -700.0 && n * p <= 64.0) {
+    double pk = exp(l0), F = pk, k = 0.0;
+    while (F < q && k < n) {
+      pk *= (n - k) / (k + 1.0) * odds;
+      k += 1.0;
+      F += pk;
+    }
+    return k;
+  }
+  // start near the quantile, build cdf(k0) by summing the pmf downwards, then walk
+  const double mean = n * p, sd = sqrt(n * p * (1.0 - p));
+  const double z = ndtri(q);
+  double k = floor(mean + z * sd + (1.0 - 2.0 * p) * (z * z - 1.0) / 6.0);
+  if (k < 0.0) k = 0.0;
+  if (k > n) k = n;
+  const double lp = lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0) + k * log(p) + (n - k) * log1p(-p);
+  const double pk0 = exp(lp);
+  double F = 0.0;
+  {
+    double t = pk0, j = k;
+    while (true) {  // pmf(j-1) = pmf(j) * j / (n-j+1) / odds
+      F += t;
+      if (j <= 0.0 || t <= 1e-18 * F) break;
+      t *= j / (n - j + 1.0) / odds;
+      j -= 1.0;
+    }
+  }
+  double pk = pk0;
+  if (F >= q) {
+    while (k > 0.0) {
+      const double Fm = F - pk;
+      if (!(Fm >= q)) break;
+      F = Fm;
+      pk *= k / (n - k + 1.0) / odds;
+      k -= 1.0;
+    }
+    return k;
+  }
+  while (F < q && k < n) {
+    pk *= (n - k) / (k + 1.0) * odds;
+    k += 1.0;
+    F += pk;
+  }
+  return k;
+}
+
+}  // namespace pbl

@@ -110,6 +110,13 @@ class QMCEngine:
     def _generate(self, n, launch, device):
         """launch(out_ptr, row_stride, col_stride, stream) writes the (n, d) block column-major."""
         n, d = int(n), self.d
+        if device == "columns":  # torch-free device buffer (what the graph evaluator consumes)
+            from ._device import DeviceColumns
+
+            cols = DeviceColumns(n, d)
+            if n and d:
+                launch(C.c_void_p(cols.ptr), 1, n, None)
+            return cols
         if device:
             import torch
             buf = torch.empty((d, n), dtype=torch.float64, device="cuda")

@@ -1,0 +1,98 @@
+"""CPU tests of the modeling-graph path: the oracle restatement is pinned to the unmodified
+reference's golden vectors, and the host compiler of probabilit_b200.modeling is run end to end
+against the same vectors with the CUDA kernel replaced by the oracle's bytecode VM."""
+import os
+
+import numpy as np
+import pytest
+
+import fake_device
+import graph_recipes
+from oracle import iman_conover as oic
+from oracle import modeling as omod
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_reference.npz"))
+
+
+def ic_correlate(X, C):
+    return oic.iman_conover(X, C)
+
+
+class OracleImanConover:
+    """A 'foreign' correlator following the reference protocol (modeling.py:577-581)."""
+
+    def set_target(self, C):
+        self.C = C
+        return self
+
+    def __call__(self, X):
+        return oic.iman_conover(X, self.C)
+
+
+@pytest.mark.parametrize("name", list(graph_recipes.RECIPES))
+def test_oracle_matches_reference_golden(name):
+    import probabilit_b200.modeling as m
+
+    recipe, n = graph_recipes.RECIPES[name]
+    sink, named = recipe(m)
+    samples = omod.evaluate(sink, GOLDEN[f"{name}__quantiles"], correlate=ic_correlate)
+    for label, node in named:
+        want = GOLDEN[f"{name}__{label}"]
+        got = samples[node]
+        assert got.dtype == want.dtype, (label, got.dtype, want.dtype)
+        np.testing.assert_array_equal(got, want, err_msg=f"{name}:{label}")
+
+
+@pytest.mark.parametrize("name", list(graph_recipes.RECIPES))
+def test_compiler_with_vm_matches_reference_golden(name, monkeypatch):
+    import probabilit_b200.modeling as m
+
+    fake_device.install(monkeypatch)
+    recipe, n = graph_recipes.RECIPES[name]
+    sink, named = recipe(m)
+    result = sink.sample_from_quantiles(GOLDEN[f"{name}__quantiles"], correlator=OracleImanConover)
+    for label, node in named:
+        want = GOLDEN[f"{name}__{label}"]
+        got = node.samples_
+        assert got.dtype == want.dtype, (label, got.dtype, want.dtype)
+        np.testing.assert_array_equal(got, want, err_msg=f"{name}:{label}")
+    if type(sink).__name__ != "NoOp":
+        np.testing.assert_array_equal(result, GOLDEN[f"{name}__{named[-1][0]}"])
+
+
+def test_gc_strategy_and_constants(monkeypatch):
+    import probabilit_b200.modeling as m
+
+    fake_device.install(monkeypatch)
+    a = m.Distribution("norm")
+    inter = (a + a) ** 2 - a
+    final = m.Exp(inter)
+    q = np.random.default_rng(0).random((50, 1))
+    out = final.sample_from_quantiles(q, gc_strategy=[])
+    assert not hasattr(a, "samples_") and not hasattr(inter, "samples_")
+    final.sample_from_quantiles(q, gc_strategy=[a])
+    assert hasattr(a, "samples_") and not hasattr(inter, "samples_")
+    np.testing.assert_array_equal(out, final.samples_)
+    final.sample_from_quantiles(q)
+    two = [n for n in final.nodes() if isinstance(n, m.Constant)][0]
+    assert two.samples_.dtype == np.int64 and two.samples_.shape == (50,)
+
+
+def test_errors(monkeypatch):
+    import probabilit_b200.modeling as m
+
+    fake_device.install(monkeypatch)
+    x = m.Distribution("norm")
+    with pytest.raises(ValueError, match="Sampling this node gave non-finite values"):
+        m.Log(x - 100).sample_from_quantiles(np.full((4, 1), 0.5))
+    with pytest.raises(ValueError, match="Sampling this node gave non-finite values"):
+        x.sample_from_quantiles(np.array([[0.0], [0.5]]))  # norm.ppf(0) = -inf
+    y = m.Distribution("norm", loc=x)
+    with pytest.raises(ValueError, match="Cannot correlate variable"):
+        (x + y).correlate(x, y, corr_mat=np.eye(2)).sample_from_quantiles(np.full((4, 2), 0.5))
+    with pytest.raises(ValueError, match="is not an ancestor"):
+        x.correlate(x, m.Distribution("norm"), corr_mat=np.eye(2))
+    with pytest.raises(NotImplementedError):
+        m.Distribution("cauchy").sample_from_quantiles(np.full((4, 1), 0.5))
+    with pytest.raises(TypeError):
+        (-(x > 0)).sample_from_quantiles(np.full((4, 1), 0.5))  # numpy: boolean negative

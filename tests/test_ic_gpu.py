@@ -233,3 +233,19 @@ def test_large_n_invariants():
     assert torch.equal(Xd[:, 0], Yd[:, 0])
     R = torch.corrcoef(Yd.T).cpu().numpy()
     assert np.abs(R - C).max() < 0.01
+
+
+@pytest.mark.parametrize("shape", [(9, 2), (5000, 6), (20000, 40)])
+def test_cholesky_correlator_matches_oracle(shape):
+    """Cholesky().set_target(C)(X) (reference correlation.py:205-285): float output, 1e-12."""
+    from probabilit_b200 import Cholesky
+
+    rng = np.random.default_rng(4)
+    N, K = shape
+    X = rng.normal(size=shape) * rng.uniform(0.5, 3, K) + rng.uniform(-5, 200, K)
+    C = random_target(rng, K) if K > 2 else np.array([[1, 0.7], [0.7, 1]])
+    want = oic.cholesky_correlator(X, C)
+    got = Cholesky().set_target(C)(X)
+    assert got.shape == want.shape and got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(np.corrcoef(got, rowvar=False), C, atol=1e-10)

@@ -88,3 +88,14 @@ def test_ndtri_restatement_is_bit_identical_to_scipy():
     assert ulp.max() <= 4
     assert np.mean(vec != ref) < 1e-3
     assert ndtri_scalar(0.0) == -np.inf and ndtri_scalar(1.0) == np.inf
+
+
+def test_cholesky_correlator_doctest_goldens():
+    """Reference doctest correlation.py:216-238 (values quoted there)."""
+    C = np.array([[1, 0.7], [0.7, 1]])
+    X = np.random.default_rng(4).normal(size=(9, 2))
+    assert sp.stats.pearsonr(*X.T).statistic.round(6) == -0.025582
+    Y = oic.cholesky_correlator(X, C)
+    assert sp.stats.pearsonr(*Y.T).statistic.round(6) == 0.7
+    np.testing.assert_allclose(np.mean(Y, axis=0), [-0.63531692, 0.70114825], atol=5e-9)
+    np.testing.assert_allclose(np.std(Y, axis=0), [1.11972638, 0.75668173], atol=5e-9)
