@@ -296,14 +296,61 @@ __device__ __noinline__ double poisson_ppf_core(double q, double mu) {
   return k;
 }
 
-// binom(n, p)._ppf(q) for 0 < q < 1, integer n >= 0, 0 <= p <= 1:  min{k : cdf(k) >= q}
+// ---- binomial pmf after C. Loader, "Fast and accurate computation of binomial probabilities"
+// (2000): saddle-point form with the Stirling error and the deviance term, accurate to a few ulp
+// for any n (a plain lgamma difference loses log10(n log n) digits).
+__device__ __forceinline__ double stirlerr(double n) {
+  // log(n!) - log(sqrt(2 pi n) (n/e)^n)
+  if (n <= 15.0) return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - 0.918938533204672741780329736406;
+  const double nn = n * n;
+  if (n > 500.0) return (1.0 / 12.0 - (1.0 / 360.0) / nn) / n;
+  if (n > 80.0) return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0) / nn) / nn) / n;
+  if (n > 35.0) return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0) / nn) / nn) / nn) / n;
+  return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0) / nn) / nn) / nn) / nn) / n;
+}
+__device__ __forceinline__ double bd0(double x, double np) {
+  // x log(x/np) + np - x, without cancellation when x ~ np
+  if (fabs(x - np) < 0.1 * (x + np)) {
+    double v = (x - np) / (x + np);
+    double s = (x - np) * v;
+    double ej = 2.0 * x * v;
+    v = v * v;
+    for (int j = 1; j < 1000; ++j) {
+      ej *= v;
+      const double s1 = s + ej / (double)(2 * j + 1);
+      if (s1 == s) return s1;
+      s = s1;
+    }
+    return s;
+  }
+  return x * log(x / np) + np - x;
+}
+__device__ __noinline__ double binom_pmf(double x, double n, double p) {
+  const double q = 1.0 - p;
+  if (x == 0.0) return exp(n * log1p(-p));
+  if (x == n) return exp(n * log(p));
+  const double lc = stirlerr(n) - stirlerr(x) - stirlerr(n - x) - bd0(x, n * p) - bd0(n - x, n * q);
+  return exp(lc) * sqrt(n / (6.283185307179586476925286766559 * x * (n - x)));
+}
+
+// binom(n, p)._ppf(q) for 0 < q < 1, integer n >= 0, 0 <= p <= 1:  min{k : cdf(k) >= q}.
+// Two-sided walk from the mode: towards the relevant tail until the pmf no longer matters next to
+// the target mass, then back, accumulating the tail mass from its small end (no cancellation in
+// either tail; the upper tail works on 1 - q, which is exact for q >= 0.5).
 __device__ __noinline__ double binom_ppf_core(double q, double n, double p) {
   if (n == 0.0 || p == 0.0) return 0.0;
   if (p == 1.0) return n;
   const double odds = p / (1.0 - p);
-  const double l0 = n * log1p(-p);  // log pmf(0)
-  if (l0 > -700.0 && n * p <= 64.0) {
-    double pk = exp(l0), F = pk, k = 0.0;
+  double k = floor((n + 1.0) * p);
+  if (k > n) k = n;
+  double pk = binom_pmf(k, n, p);
+  if (q <= 0.5) {
+    const double stop = fmax(q * 1e-20, 1e-300);
+    while (k > 0.0 && pk > stop) {  // pmf(k-1) = pmf(k) * k / (n-k+1) / odds
+      pk *= k / (n - k + 1.0) / odds;
+      k -= 1.0;
+    }
+    double F = pk;
     while (F < q && k < n) {
       pk *= (n - k) / (k + 1.0) * odds;
       k += 1.0;
@@ -311,39 +358,19 @@ __device__ __noinline__ double binom_ppf_core(double q, double n, double p) {
     }
     return k;
   }
-  // start near the quantile, build cdf(k0) by summing the pmf downwards, then walk
-  const double mean = n * p, sd = sqrt(n * p * (1.0 - p));
-  const double z = ndtri(q);
-  double k = floor(mean + z * sd + (1.0 - 2.0 * p) * (z * z - 1.0) / 6.0);
-  if (k < 0.0) k = 0.0;
-  if (k > n) k = n;
-  const double lp = lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0) + k * log(p) + (n - k) * log1p(-p);
-  const double pk0 = exp(lp);
-  double F = 0.0;
-  {
-    double t = pk0, j = k;
-    while (true) {  // pmf(j-1) = pmf(j) * j / (n-j+1) / odds
-      F += t;
-      if (j <= 0.0 || t <= 1e-18 * F) break;
-      t *= j / (n - j + 1.0) / odds;
-      j -= 1.0;
-    }
-  }
-  double pk = pk0;
-  if (F >= q) {
-    while (k > 0.0) {
-      const double Fm = F - pk;
-      if (!(Fm >= q)) break;
-      F = Fm;
-      pk *= k / (n - k + 1.0) / odds;
-      k -= 1.0;
-    }
-    return k;
-  }
-  while (F < q && k < n) {
+  const double s = 1.0 - q;  // want min k with P(X > k) <= s
+  const double stop = fmax(s * 1e-20, 1e-300);
+  while (k < n && pk > stop) {
     pk *= (n - k) / (k + 1.0) * odds;
     k += 1.0;
-    F += pk;
+  }
+  double S = 0.0;  // P(X > k), the mass above the walk's end is negligible next to s
+  while (k > 0.0) {
+    const double Sn = S + pk;  // P(X > k-1)
+    if (!(Sn <= s)) break;
+    S = Sn;
+    pk *= k / (n - k + 1.0) / odds;
+    k -= 1.0;
   }
   return k;
 }
