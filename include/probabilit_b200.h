@@ -188,9 +188,21 @@ typedef enum pbl_graph_op {
   PBL_OP_TANH = 82, PBL_OP_ASINH = 83, PBL_OP_ACOSH = 84, PBL_OP_ATANH = 85, PBL_OP_NOT = 86
 } pbl_graph_op;
 
+/* Flags or-ed into pbl_graph_instr.op of a computing instruction (ppf / arithmetic / MOV) so that the
+ * common load -> ppf -> check -> store chain of one node is ONE interpreted instruction:
+ *   Q_INPUT    (ppf only) operand 0 is inputs[src[0]][row] instead of a slot
+ *   Q_UNIFORM  (ppf only) operand 0 is the Philox uniform of column src[0], seed bits in imm[0]
+ *   CHECK      after computing: if the result is not finite report node tag (dst >> 8) & 0xFFF
+ *   STORE      after computing: outputs[dst >> 20][row] <- result
+ * dst & 0xFF is the destination slot. */
+#define PBL_GRAPH_Q_INPUT 0x100
+#define PBL_GRAPH_Q_UNIFORM 0x200
+#define PBL_GRAPH_CHECK 0x400
+#define PBL_GRAPH_STORE 0x800
+
 typedef struct pbl_graph_instr {
-  int32_t op;     /* pbl_graph_op */
-  int32_t dst;    /* destination slot */
+  int32_t op;     /* pbl_graph_op | PBL_GRAPH_* flags */
+  int32_t dst;    /* destination slot | check tag << 8 | output index << 20 */
   int32_t src[4]; /* slot index, or < 0: imm[i] */
   double imm[4];
 } pbl_graph_instr;

@@ -73,7 +73,17 @@ def run(program, n_slots, n, inputs, outputs, uniform=None):
 
     with np.errstate(all="ignore"):
         for ins in program:
-            name = NAME[ins.op]
+            name = NAME[ins.op & 0xFF]
+            flags, dst, tag, oidx = ins.op, ins.dst & 0xFF, (ins.dst >> 8) & 0xFFF, (ins.dst & 0xFFFFFFFF) >> 20
+
+            def finish(value):
+                nonlocal bad
+                slots[dst] = value
+                if flags & 0x400 and not np.all(np.isfinite(value)):
+                    bad = tag if bad < 0 else min(bad, tag)
+                if flags & 0x800:
+                    outputs[oidx][:] = value
+
             if name == "LOAD":
                 slots[ins.dst] = np.array(inputs[ins.src[0]], dtype=np.float64)
             elif name == "STORE":
@@ -82,16 +92,21 @@ def run(program, n_slots, n, inputs, outputs, uniform=None):
                 if not np.all(np.isfinite(slots[ins.src[0]])):
                     bad = ins.src[1] if bad < 0 else min(bad, ins.src[1])
             elif name == "MOV":
-                slots[ins.dst] = operand(ins, 0).copy()
+                finish(operand(ins, 0).copy())
             elif name == "UNIFORM":
                 slots[ins.dst] = uniform(ins.src[0])
             elif name.startswith("PPF_"):
-                q = operand(ins, 0)
-                slots[ins.dst] = np.asarray(ppf(name, q, [operand(ins, i) for i in (1, 2, 3)]), dtype=np.float64)
+                if flags & 0x100:
+                    q = np.array(inputs[ins.src[0]], dtype=np.float64)
+                elif flags & 0x200:
+                    q = uniform(ins.src[0])
+                else:
+                    q = operand(ins, 0)
+                finish(np.asarray(ppf(name, q, [operand(ins, i) for i in (1, 2, 3)]), dtype=np.float64))
             elif name in BINARY:
-                slots[ins.dst] = np.asarray(BINARY[name](operand(ins, 0), operand(ins, 1)), dtype=np.float64)
+                finish(np.asarray(BINARY[name](operand(ins, 0), operand(ins, 1)), dtype=np.float64))
             elif name in UNARY:
-                slots[ins.dst] = np.asarray(UNARY[name](operand(ins, 0)), dtype=np.float64)
+                finish(np.asarray(UNARY[name](operand(ins, 0)), dtype=np.float64))
             elif name != "NOP":
                 raise ValueError(f"unknown opcode {ins.op}")
     return bad

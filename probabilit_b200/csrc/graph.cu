@@ -194,25 +194,36 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
     const bool active = row < g.n;
     for (int pc = 0; pc < g.n_instr; ++pc) {
       const pbl_graph_instr& in = prog[pc];
-      const int op = in.op;
+      const int op = in.op & 0xFF, flags = in.op;
+      const int dst = in.dst & 0xFF;
       const int s0 = in.src[0], s1 = in.src[1];
       if (op < 16) {
         if (op == PBL_OP_LOAD) {
-          SLOT(in.dst) = active ? ld_stream_f64(g.inputs[s0] + row) : 0.5;
+          SLOT(dst) = active ? ld_stream_f64(g.inputs[s0] + row) : 0.5;
         } else if (op == PBL_OP_STORE) {
           if (active) __stcs(g.outputs[s1] + row, SLOT(s0));
         } else if (op == PBL_OP_CHECK) {
           const double v = SLOT(s0);
           if (active && !isfinite(v)) atomicMin(g.first_nonfinite, s1);
         } else if (op == PBL_OP_MOV) {
-          SLOT(in.dst) = s0 >= 0 ? SLOT(s0) : in.imm[0];
+          const double v = s0 >= 0 ? SLOT(s0) : in.imm[0];
+          SLOT(dst) = v;
+          if ((flags & PBL_GRAPH_STORE) && active) __stcs(g.outputs[(uint32_t)in.dst >> 20] + row, v);
         } else if (op == PBL_OP_UNIFORM) {
           const uint64_t seed = (uint64_t)__double_as_longlong(in.imm[0]);
-          SLOT(in.dst) = philox_uniform_at(seed, g.row0 + (uint64_t)(active ? row : 0), (uint32_t)s0);
+          SLOT(dst) = philox_uniform_at(seed, g.row0 + (uint64_t)(active ? row : 0), (uint32_t)s0);
         }
         continue;
       }
-      const double a = s0 >= 0 ? SLOT(s0) : in.imm[0];
+      double a;
+      if (flags & PBL_GRAPH_Q_INPUT) {  // fused LOAD: the quantile comes straight from its column
+        a = active ? ld_stream_f64(g.inputs[s0] + row) : 0.5;
+      } else if (flags & PBL_GRAPH_Q_UNIFORM) {  // fused UNIFORM: generated in-kernel
+        a = philox_uniform_at((uint64_t)__double_as_longlong(in.imm[0]), g.row0 + (uint64_t)(active ? row : 0),
+                              (uint32_t)s0);
+      } else {
+        a = s0 >= 0 ? SLOT(s0) : in.imm[0];
+      }
       double r;
       if (op >= 64) {  // unary
         switch (op) {
@@ -245,7 +256,11 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
           r = eval_ppf(op, a, p0, p1, p2);
         }
       }
-      SLOT(in.dst) = r;
+      SLOT(dst) = r;
+      if (active) {
+        if ((flags & PBL_GRAPH_CHECK) && !isfinite(r)) atomicMin(g.first_nonfinite, (in.dst >> 8) & 0xFFF);
+        if (flags & PBL_GRAPH_STORE) __stcs(g.outputs[(uint32_t)in.dst >> 20] + row, r);
+      }
     }
   }
 #undef SLOT
@@ -277,13 +292,17 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
   }
   for (int i = 0; i < n_instr; ++i) {  // validate every operand before it reaches the device
     const pbl_graph_instr& in = program[i];
-    bool ok = in.dst >= 0 && in.dst < std::max(n_slots, 1);
-    const int nsrc = in.op == PBL_OP_STORE || in.op == PBL_OP_CHECK || in.op == PBL_OP_LOAD ||
-                             in.op == PBL_OP_UNIFORM ? 0 : 4;
-    for (int s = 0; s < nsrc; ++s) ok = ok && in.src[s] < n_slots;
-    if (in.op == PBL_OP_LOAD) ok = ok && in.src[0] >= 0 && in.src[0] < n_inputs;
-    if (in.op == PBL_OP_STORE) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0 && in.src[1] < n_outputs;
-    if (in.op == PBL_OP_CHECK) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0;
+    const int op = in.op & 0xFF;
+    bool ok = (in.dst & 0xFF) < std::max(n_slots, 1) && in.dst >= 0;
+    const bool fused_q = (in.op & (PBL_GRAPH_Q_INPUT | PBL_GRAPH_Q_UNIFORM)) != 0;
+    const int nsrc = op == PBL_OP_STORE || op == PBL_OP_CHECK || op == PBL_OP_LOAD || op == PBL_OP_UNIFORM ? 0 : 4;
+    for (int s = fused_q ? 1 : 0; s < nsrc; ++s) ok = ok && in.src[s] < n_slots;
+    if (op == PBL_OP_LOAD || (in.op & PBL_GRAPH_Q_INPUT)) ok = ok && in.src[0] >= 0 && in.src[0] < n_inputs;
+    if (fused_q) ok = ok && op >= PBL_PPF_NORM && op <= PBL_PPF_BERNOULLI && in.src[0] >= 0;
+    if (in.op & PBL_GRAPH_STORE) ok = ok && (int)((uint32_t)in.dst >> 20) < n_outputs && (op >= 16 || op == PBL_OP_MOV);
+    if (in.op & PBL_GRAPH_CHECK) ok = ok && op >= 16;
+    if (op == PBL_OP_STORE) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0 && in.src[1] < n_outputs;
+    if (op == PBL_OP_CHECK) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0;
     if (!ok) {
       pbl::set_last_error("pbl_graph_eval_f64: instruction " + std::to_string(i) + " has an operand out of range");
       return kBadShape;

@@ -615,9 +615,45 @@ class _Emitter:
         return _Val(vreg=d, dtype=dtype)
 
     # -- register allocation: virtual registers -> shared-memory slots -------------------------
+    def fuse(self):
+        """Peephole pass: fold LOAD / UNIFORM into the ppf that consumes the quantile, and CHECK / STORE
+        into the instruction that produced the value (flags of include/probabilit_b200.h), so that one
+        node costs one interpreted instruction."""
+        readers, definer = {}, {}
+        for i, (op, d, srcs, imms, aux, *_) in enumerate(self.instrs):
+            if d is not None:
+                definer[d] = i
+            for v in [x for x in srcs if x is not None] + ([aux[1]] if aux and aux[0] in ("store", "check") else []):
+                readers.setdefault(v, []).append(i)
+        drop = set()
+        for i, ins in enumerate(self.instrs):
+            op, d, srcs, imms, aux = ins[:5]
+            if op in (OP["LOAD"], OP["UNIFORM"]) and len(readers.get(d, [])) == 1:
+                j = readers[d][0]
+                tgt = self.instrs[j]
+                if 16 <= (tgt[0] & 0xFF) < 32 and tgt[2][0] == d and d not in tgt[2][1:]:
+                    tgt[0] |= 0x100 if op == OP["LOAD"] else 0x200
+                    tgt[2][0] = None
+                    tgt[3][0] = imms[0]
+                    tgt.append(("q", aux[1]))  # column index, resolved in assemble()
+                    drop.add(i)
+            elif aux and aux[0] in ("store", "check"):
+                j = definer.get(aux[1])
+                if j is None:
+                    continue
+                tgt = self.instrs[j]
+                base = tgt[0] & 0xFF
+                flag = 0x800 if aux[0] == "store" else 0x400
+                if (base >= 16 or (base == OP["MOV"] and aux[0] == "store")) and not (tgt[0] & flag):
+                    tgt[0] |= flag
+                    tgt.append((aux[0], aux[2]))
+                    drop.add(i)
+        self.instrs = [ins for i, ins in enumerate(self.instrs) if i not in drop]
+
     def assemble(self):
+        self.fuse()
         reads = []
-        for op, d, srcs, imms, aux in self.instrs:
+        for op, d, srcs, imms, aux, *extra in self.instrs:
             r = [s for s in srcs if s is not None]
             if aux and aux[0] in ("store", "check"):
                 r.append(aux[1])
@@ -628,7 +664,7 @@ class _Emitter:
                 last[v] = i
         free, slot_of, n_slots = [], {}, 0
         prog = (_lib.GraphInstr * len(self.instrs))()
-        for i, (op, d, srcs, imms, aux) in enumerate(self.instrs):
+        for i, (op, d, srcs, imms, aux, *extra) in enumerate(self.instrs):
             ins = prog[i]
             ins.op = op
             for j in range(4):
@@ -654,6 +690,13 @@ class _Emitter:
                 ins.dst = s
                 if d not in last:  # never read: the slot is free again right away
                     free.append(s)
+            for kind, value in extra:  # fused flags
+                if kind == "q":
+                    ins.src[0] = value
+                elif kind == "check":
+                    ins.dst |= (value & 0xFFF) << 8
+                elif kind == "store":
+                    ins.dst |= value << 20
         if n_slots > MAX_SLOTS:
             raise NotImplementedError(f"graph needs {n_slots} live values per sample; the kernel holds {MAX_SLOTS}")
         if len(self.instrs) > MAX_INSTR:
@@ -767,7 +810,7 @@ class _GraphRun:
         # main program, nodes in topological order (reference :586-612)
         em = _Emitter()
         value_of = {node: _Val(arr=arr) for node, arr in folded.items() if arr is not None}
-        keep, const_fail = [], None
+        keep, const_fail, n_stored = [], None, 0
         for tag, node in enumerate(topo):
             if node in folded:
                 arr = folded[node]
@@ -792,6 +835,9 @@ class _GraphRun:
                 em.check(val, tag)
             if self.retained(node):
                 keep.append((node, val))
+                if not val.is_imm and node not in corr_index:
+                    em.store(val, n_stored)  # right away: the slot is free again after its last use
+                    n_stored += 1
 
         # inputs: quantile columns first, then the correlated columns
         nq = 0 if self.qcols is None else self.qcols.k
@@ -804,9 +850,8 @@ class _GraphRun:
             inputs += [corr_cols.column_ptr(j) for j in range(corr_cols.k)]
 
         stored = [(node, val) for node, val in keep if not val.is_imm and node not in corr_index]
+        assert len(stored) == n_stored
         out_cols = DeviceColumns(n, len(stored)) if stored else None
-        for j, (node, val) in enumerate(stored):
-            em.store(val, j)
         outputs = [out_cols.column_ptr(j) for j in range(len(stored))]
         bad = _run_program(em, n, 0, inputs, outputs)
         if const_fail is not None and (bad < 0 or const_fail < bad):

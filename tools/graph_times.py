@@ -25,8 +25,8 @@ for label, kwargs in (("philox_sink_only", dict(gc_strategy=[])), ("philox_all_n
         res = sink.sample(n, random_state=rep, **kwargs)
         ts.append(time.perf_counter() - t0)
     out[label] = {"wall_s_incl_d2h_of_sink": ts, "mean": float(res.mean())}
-q = qmc.Sobol(d=20, seed=0).random(n, device="columns")
-for label, kwargs in (("sobol_quantiles_sink_only", dict(gc_strategy=[])),):
+q = qmc.PhiloxUniform(d=20, seed=0).random(n, device="columns")
+for label, kwargs in (("supplied_quantiles_sink_only", dict(gc_strategy=[])),):
     ts = []
     for rep in range(3):
         lib.pbl_stream_synchronize(None)
