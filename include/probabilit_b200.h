@@ -87,6 +87,27 @@ PBL_API int pbl_cholesky_plan_run(pbl_ic_plan* plan, const double* X_dev, int64_
                                   int64_t x_col_stride, double* Y_dev, int64_t y_row_stride,
                                   int64_t y_col_stride, void* stream);
 
+/* ---- PermutationCorrelator, reference correlation.py:473-703 with CorrelationMatrix :757-921 ----
+ * begin : Y <- X (column-major [k][n], caller-owned), CorrelationMatrix.__init__ (:819-853) on it
+ *         (spearman != 0: on rankdata(X), needs a plan with sort workspace).  target / weights are
+ *         HOST k*k row-major (weights already normalised to sum 1, :592-593).
+ *         PBL_NOT_POSITIVE_DEFINITE here means "X has one or several constant columns" (:847-848).
+ * steps : run n_steps hill-climbing steps in ONE launch.  Step t works on column step_col[t] with the
+ *         swap lists i = swaps[2*step_off[t] .. +step_cnt[t]), j = the next step_cnt[t] entries -- the
+ *         host draws them exactly like SwapIndexGenerator (:428-470) so the accept/reject sequence is
+ *         the reference's.  After every step on column 0 the weighted RMSE (:597-601) is compared with
+ *         tol (:689-697); errors[0] = error before the first step, errors[1..] = after each check.
+ * corr  : the running correlation matrix (k*k, host), for tests. */
+PBL_API int pbl_permcorr_begin(pbl_ic_plan* plan, const double* X_dev, int64_t x_row_stride,
+                               int64_t x_col_stride, double* Y_dev, int32_t spearman, const double* target,
+                               const double* weights, void* stream);
+PBL_API int pbl_permcorr_steps(pbl_ic_plan* plan, double* Y_dev, const int32_t* step_col,
+                               const int32_t* step_off, const int32_t* step_cnt, const int64_t* swaps,
+                               int64_t n_swaps_total, int64_t n_steps, double tol, int64_t* steps_done,
+                               int32_t* converged, double* errors, int64_t errors_cap, int64_t* n_errors,
+                               void* stream);
+PBL_API int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr);
+
 /* Same call with HOST buffers (what a NumPy caller holds): copies X to the device, runs, copies Y
  * back.  X and Y must each be one contiguous block in C or F order. */
 PBL_API int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t x_row_stride,

@@ -4,6 +4,7 @@ Public names mirror the reference's (src/probabilit/correlation.py); the compute
 libprobabilit_b200.so (hand-written sm_100a CUDA behind a C ABI, include/probabilit_b200.h).
 """
 from .correlation import (Cholesky, Correlator, CorrelatorError, ImanConover,  # noqa: F401
-                          nearest_correlation_matrix)
+                          PermutationCorrelator, nearest_correlation_matrix)
 
-__all__ = ["Cholesky", "Correlator", "CorrelatorError", "ImanConover", "nearest_correlation_matrix"]
+__all__ = ["Cholesky", "Correlator", "CorrelatorError", "ImanConover", "PermutationCorrelator",
+           "nearest_correlation_matrix"]

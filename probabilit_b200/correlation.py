@@ -347,3 +347,167 @@ class Cholesky(_PlanCorrelator):
         if st == _lib.STATUS_NOT_PD:
             raise np.linalg.LinAlgError("Matrix is not positive definite")  # np.linalg.cholesky(cov), :271
         _raise_for_status(st)
+
+
+class SwapIndexGenerator:
+    """Disjoint swap index pairs drawn from a NumPy generator exactly like the reference's
+    (correlation.py:428-470): consumes one ``rng.permutation(n)`` 2*size entries at a time and
+    re-draws when it runs out.  Host control plane: this stream *is* the reference's stream, which
+    is what makes the device hill climb reproduce the reference's accept/reject sequence."""
+
+    def __init__(self, rng, n):
+        assert n >= 2
+        self.rng = rng
+        self.indices = np.arange(n)
+        self.permutation = self.rng.permutation(self.indices)
+
+    def __call__(self, size):
+        assert size >= 1
+        size = min(size, len(self.indices) // 2)
+        chosen, self.permutation = self.permutation[: 2 * size], self.permutation[2 * size:]
+        if len(chosen) < 2 * size:
+            self.permutation = self.rng.permutation(self.indices)
+            return self(size)
+        return chosen[:size], chosen[size:]
+
+
+class PermutationCorrelator(Correlator):
+    """Randomised hill climbing on row swaps within each column (reference correlation.py:473-703),
+    executed as one persistent CUDA block per chunk of steps (csrc/permcorr.cu) with the incremental
+    correlation update of the reference's ``CorrelationMatrix`` (:757-921).
+
+    Same constructor and call signature as the reference.  The swap proposals are the reference's own
+    NumPy stream (``SwapIndexGenerator``), so for the same ``seed`` the result equals the
+    reference's entry for entry."""
+
+    _CHUNK_STEPS = 1 << 16  # steps per launch (bounds the host-side index staging)
+
+    def __init__(self, *, weights=None, iterations=1000, tol=0.01, correlation_type="pearson", seed=None,
+                 verbose=False, device=None):
+        if not (weights is None or np.all(weights > 0)):
+            raise ValueError("`weights` must have positive entries.")
+        if not (isinstance(iterations, int) and iterations >= 0):
+            raise ValueError("`iterations` must be non-negative integer.")
+        if not isinstance(tol, float) and tol > 0:
+            raise ValueError("`tol` must be a positive float.")
+        if not (seed is None or isinstance(seed, int)):
+            raise TypeError("`seed` must be None or an integer")
+        if not isinstance(verbose, bool):
+            raise TypeError("`verbose` must be boolean")
+        self.iters = iterations
+        self.tol = tol
+        self.rng = np.random.default_rng(seed)
+        self.verbose = verbose
+        self.correlation_type = correlation_type
+        self.device = device
+
+    def set_target(self, correlation_matrix, *, weights=None):
+        super().set_target(correlation_matrix)
+        weights = np.ones_like(self.C) if weights is None else weights
+        self.weights = weights / np.sum(weights)
+        self.triu_indices = np.triu_indices(self.C.shape[0], k=1)
+        return self
+
+    def _error(self, observed, target):
+        """RMSE over the upper triangle of corr(X) - target (reference :597-601); K x K, host."""
+        idx = self.triu_indices
+        return float(np.sqrt(np.sum(self.weights[idx] * (observed[idx] - target[idx]) ** 2.0)))
+
+    @staticmethod
+    def subiters(n, i):
+        """Swaps per step: long swap lists early, single swaps for the last half (reference :603-617)."""
+        C = np.log2(n) + 1
+        return int(np.ceil(C ** (1 - (2 * i / n))))
+
+    def __call__(self, X):
+        self._validate_X(X, check_rows_cols=False)
+        if not (isinstance(X, np.ndarray) and X.ndim == 2):
+            raise ValueError("`X` must be a 2D numpy array.")
+        if self.correlation_type not in ("pearson", "spearman"):
+            raise ValueError(f"`correlation_type` must be in ('pearson', 'spearman'), got {self.correlation_type}")
+        import copy as _copy
+        from ._device import DeviceColumns
+
+        lib = _lib.require_gpu()
+        N, K = X.shape
+        if N < 2:
+            raise AssertionError("need at least two observations")
+        if self.verbose:
+            print(f"Running permutation correlator for {self.iters if self.iters else 'inf'} iterations.")
+        device = 0 if self.device is None else int(self.device)
+        spearman = self.correlation_type == "spearman"
+        plan = _IcPlan(N, K, device, rows_only=not spearman)
+        dX = DeviceColumns.from_host(X)
+        dY = DeviceColumns(N, K)
+        try:
+            target = np.ascontiguousarray(self.C, dtype=np.float64)
+            weights = np.ascontiguousarray(self.weights, dtype=np.float64)
+            st = _lib.check(lib.pbl_permcorr_begin(plan.handle, C.c_void_p(dX.ptr), 1, N, C.c_void_p(dY.ptr),
+                                                   1 if spearman else 0, target.ctypes.data, weights.ctypes.data,
+                                                   None), "pbl_permcorr_begin")
+            if st == _lib.STATUS_NOT_PD:
+                raise ValueError("X has one or several constant columns")  # correlation.py:847-848
+            _raise_for_status(st)
+            swaps_gen = SwapIndexGenerator(rng=self.rng, n=N)
+            n_sched = self.iters if self.iters else 10_000
+            iters_per_chunk = max(1, self._CHUNK_STEPS // K)
+            iteration, finished = 1, False
+            while not finished and (not self.iters or iteration <= self.iters):
+                last = iteration + iters_per_chunk - 1
+                if self.iters:
+                    last = min(last, self.iters)
+                snapshot = _copy.deepcopy(swaps_gen)  # to replay the exact consumption on early exit
+                cols, offs, cnts, idx, counts_per_iter = [], [], [], [], []
+                total = 0
+                for it in range(iteration, last + 1):
+                    num_swaps = self.subiters(n=n_sched, i=it)
+                    counts_per_iter.append(num_swaps)
+                    for k in range(K):
+                        i, j = swaps_gen(num_swaps)
+                        cols.append(k)
+                        offs.append(total)
+                        cnts.append(len(i))
+                        idx.append(i)
+                        idx.append(j)
+                        total += len(i)
+                n_steps = len(cols)
+                cols_a = np.asarray(cols, dtype=np.int32)
+                offs_a = np.asarray(offs, dtype=np.int32)
+                cnts_a = np.asarray(cnts, dtype=np.int32)
+                idx_a = np.ascontiguousarray(np.concatenate(idx), dtype=np.int64)
+                errors = np.zeros(last - iteration + 3)
+                done, conv, nerr = C.c_int64(), C.c_int32(), C.c_int64()
+                st = _lib.check(lib.pbl_permcorr_steps(
+                    plan.handle, C.c_void_p(dY.ptr), cols_a.ctypes.data, offs_a.ctypes.data, cnts_a.ctypes.data,
+                    idx_a.ctypes.data, total, n_steps, float(self.tol), C.byref(done), C.byref(conv),
+                    errors.ctypes.data, errors.size, C.byref(nerr), None), "pbl_permcorr_steps")
+                _raise_for_status(st)
+                if self.verbose:
+                    self._print_progress(iteration, last, errors, int(nerr.value), counts_per_iter, bool(conv.value))
+                if conv.value:
+                    # leave self.rng where the reference would have left it: replay the consumed draws only
+                    swaps_gen = snapshot
+                    for t in range(int(done.value)):
+                        swaps_gen(counts_per_iter[t // K])
+                    self.rng = swaps_gen.rng
+                    finished = True
+                iteration = last + 1
+            out = dY.to_host()
+        finally:
+            dX.free()
+            dY.free()
+            plan.close()
+        result = np.ascontiguousarray(out)  # corr_mat.X is X.copy(): C order (reference :831)
+        return result if result.dtype == X.dtype else result.astype(X.dtype)
+
+    def _print_progress(self, first, last, errors, nerr, counts, converged):
+        # errors[0] = before the chunk, errors[t] = after the check of the t-th iteration of the chunk
+        every = self.iters // 10 if self.iters else 1000
+        for t, it in enumerate(range(first, first + max(nerr - 1, 0) + (0 if converged else 0))):
+            if it > last:
+                break
+            if every and it % every == 0 and t < len(errors):
+                print(f" Iter {it:>6}  Error: {errors[t]:.6f} Swaps: {counts[t]:>2}")
+        if converged and nerr >= 1:
+            it = first + nerr - 2
+            print(f" Terminating at iteration {it} due to tolerance. Error: {errors[nerr - 1]:.6f}")

@@ -124,6 +124,24 @@ int pbl_cholesky_plan_run(pbl_ic_plan* plan, const double* X, int64_t xrs, int64
   return pbl::cholesky_correlator_run(plan->impl, X, xrs, xcs, Y, yrs, ycs, (cudaStream_t)stream);
 }
 
+int pbl_permcorr_begin(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, double* Y, int32_t spearman,
+                       const double* target, const double* weights, void* stream) {
+  if (!plan || !X || !Y || !target || !weights) return kBadShape;
+  return pbl::permcorr_begin(plan->impl, X, xrs, xcs, Y, spearman, target, weights, (cudaStream_t)stream);
+}
+int pbl_permcorr_steps(pbl_ic_plan* plan, double* Y, const int32_t* step_col, const int32_t* step_off,
+                       const int32_t* step_cnt, const int64_t* swaps, int64_t n_swaps_total, int64_t n_steps,
+                       double tol, int64_t* steps_done, int32_t* converged, double* errors, int64_t errors_cap,
+                       int64_t* n_errors, void* stream) {
+  if (!plan || !Y || (n_steps > 0 && (!step_col || !step_off || !step_cnt || !swaps))) return kBadShape;
+  return pbl::permcorr_steps(plan->impl, Y, step_col, step_off, step_cnt, swaps, n_swaps_total, n_steps, tol,
+                             steps_done, converged, errors, errors_cap, n_errors, (cudaStream_t)stream);
+}
+int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr) {
+  if (!plan || !corr) return kBadShape;
+  return pbl::permcorr_read_corr(plan->impl, corr);
+}
+
 static bool contiguous_layout(int64_t n, int32_t k, int64_t rs, int64_t cs) {
   return (rs == 1 && cs == n) || (cs == 1 && rs == k) || (n == 1 && cs == 1) || (k == 1 && rs == 1);
 }

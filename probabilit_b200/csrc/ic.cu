@@ -264,7 +264,11 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
       }
       const uint32_t row = s_row[kHalo + p];
       rows_out[g] = row & kRowMask;
-      if (MODE == 0) {
+      if (MODE == 2) {
+        // scipy.stats.rankdata(x) itself (average ranks as doubles): the Spearman mode of
+        // CorrelationMatrix, correlation.py:835-837
+        stage[g] = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
+      } else if (MODE == 0) {
         double sc;
         if (s == e) {
           sc = ld_stream_f64(vdw + g);  // untied: the score depends on the position only
@@ -756,6 +760,7 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->P);
   cudaFree(p->gram_partials);
   cudaFree(p->moments);
+  permcorr_free(p->permcorr);
   delete p;
 }
 
@@ -775,13 +780,14 @@ static int post_sort_attr() {
   if (!done) {
     PBL_CUDA_CHECK(cudaFuncSetAttribute(post_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
     PBL_CUDA_CHECK(cudaFuncSetAttribute(post_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(post_sort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
     done = true;
   }
   return kOk;
 }
 
 int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
-                         int col0, int ncols, cudaStream_t stream) {
+                         int col0, int ncols, cudaStream_t stream, bool ranks_only) {
   if (p->rows_only) {
     set_last_error("this plan was created without a sort workspace (rows-only)");
     return kBadShape;
@@ -798,9 +804,14 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
                                    p->window_bits, sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
     PBL_RETURN_IF(post_sort_attr());
-    post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
-        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
+    if (ranks_only)
+      post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
+          p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
+    else
+      post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
+          p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
                                  p->use_lookback, stream));
@@ -933,6 +944,49 @@ int cholesky_correlator_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs
     set_last_error("Matrix is not positive definite");
     return kNotPositiveDefinite;
   }
+  return kOk;
+}
+
+// Column means (MODE 0) or population standard deviations about `mean` (MODE 1) of an (n, k) matrix,
+// fixed-order reductions (used by the Cholesky and permutation correlators).
+int column_moments(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, const double* mean_dev, double* out_dev,
+                   int mode, cudaStream_t stream) {
+  const int k = p->k;
+  const int64_t n = p->n;
+  if (!p->moments) {
+    PBL_CUDA_CHECK(cudaMalloc((void**)&p->moments, ((size_t)2 * k + (size_t)k * kMomBlocks) * 8));
+    p->bytes += ((size_t)2 * k + (size_t)k * kMomBlocks) * 8;
+  }
+  double* partials = p->moments + 2 * k;
+  const dim3 mg(kMomBlocks, k);
+  if (mode == 0) {
+    col_moment_kernel<0><<<mg, 256, 0, stream>>>(X, xrs, xcs, n, nullptr, partials);
+    PBL_LAUNCH_CHECK();
+    col_moment_finish_kernel<0><<<(k + 127) / 128, 128, 0, stream>>>(partials, kMomBlocks, k, (double)n, out_dev);
+  } else {
+    col_moment_kernel<1><<<mg, 256, 0, stream>>>(X, xrs, xcs, n, mean_dev, partials);
+    PBL_LAUNCH_CHECK();
+    col_moment_finish_kernel<1><<<(k + 127) / 128, 128, 0, stream>>>(partials, kMomBlocks, k, (double)n, out_dev);
+  }
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
+__global__ void __launch_bounds__(256)
+centre_kernel(const double* __restrict__ X, int64_t row_stride, int64_t col_stride, int64_t n,
+              const double* __restrict__ mean, double* __restrict__ S) {
+  const int col = blockIdx.y;
+  const double m = mean[col];
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
+    S[(int64_t)col * n + r] = ld_stream_f64(X + (int64_t)col * col_stride + r * row_stride) - m;
+}
+
+// S[c][r] = X[r, c] - mean[c]  (column-major destination)
+int centre_columns(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, const double* mean_dev, double* S,
+                   cudaStream_t stream) {
+  const unsigned rb = (unsigned)std::min<int64_t>((p->n + 255) / 256, (int64_t)num_sms() * 8);
+  centre_kernel<<<dim3(rb, p->k), 256, 0, stream>>>(X, xrs, xcs, p->n, mean_dev, S);
+  PBL_LAUNCH_CHECK();
   return kOk;
 }
 

@@ -30,6 +30,7 @@ struct IcPlan {
   double* T = nullptr;         // [k][k] row-major, upper triangular: correlated = scores @ T
   double* P = nullptr;         // [k][k] row-major lower Cholesky factor of the target C
   double* moments = nullptr;   // Cholesky correlator: [k] mean, [k] std, [k][256] partial sums (lazy)
+  void* permcorr = nullptr;    // PermutationCorrelator state (permcorr.cu), lazy
   uint32_t* flags = nullptr;   // [8], see SortFlag in sort.cuh
   size_t bytes = 0;            // device bytes held by the plan
 };
@@ -47,14 +48,30 @@ int ic_plan_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_c
 
 // Stage-level entry points (parity tests, and the multi-GPU host driver which interleaves
 // collectives between them).  All asynchronous on `stream`.
+// ranks_only: leave scipy.stats.rankdata(X[:, c]) (average ranks) in plan->scores instead of the scores
 int ic_stage_rank_scores(IcPlan* plan, const double* X, int64_t row_stride, int64_t col_stride,
-                         int col0, int ncols, cudaStream_t stream);
+                         int col0, int ncols, cudaStream_t stream, bool ranks_only = false);
 int ic_stage_gram(IcPlan* plan, cudaStream_t stream);
 int ic_stage_solve(IcPlan* plan, int64_t n_total, cudaStream_t stream);
 int ic_stage_transform(IcPlan* plan, cudaStream_t stream);
 int ic_stage_rank_gather(IcPlan* plan, double* Y, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream);
 int ic_read_status(IcPlan* plan, cudaStream_t stream);
+
+int column_moments(IcPlan* plan, const double* X, int64_t xrs, int64_t xcs, const double* mean_dev,
+                   double* out_dev, int mode, cudaStream_t stream);
+int centre_columns(IcPlan* plan, const double* X, int64_t xrs, int64_t xcs, const double* mean_dev, double* S,
+                   cudaStream_t stream);
+
+// PermutationCorrelator (permcorr.cu; reference correlation.py:473-703, :757-921)
+void permcorr_free(void* state);
+int permcorr_begin(IcPlan* plan, const double* X, int64_t xrs, int64_t xcs, double* Y, int spearman,
+                   const double* target_host, const double* weights_host, cudaStream_t stream);
+int permcorr_steps(IcPlan* plan, double* Y, const int32_t* step_col, const int32_t* step_off,
+                   const int32_t* step_cnt, const int64_t* swaps, int64_t n_swaps_total, int64_t n_steps,
+                   double tol, int64_t* steps_done, int32_t* converged, double* errors_host,
+                   int64_t errors_cap, int64_t* n_errors, cudaStream_t stream);
+int permcorr_read_corr(IcPlan* plan, double* corr_host);
 
 // Cholesky correlator (reference correlation.py:205-285); synchronous like ic_plan_run.
 int cholesky_correlator_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
