@@ -108,6 +108,13 @@ PBL_API int pbl_permcorr_steps(pbl_ic_plan* plan, double* Y_dev, const int32_t* 
                                void* stream);
 PBL_API int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr);
 
+/* ImanConover.__call__ with HOST buffers on a reusable plan: X / Y contiguous in C or F order, the
+ * caller provides device staging for n*k doubles each.  For column-major data the host<->device
+ * copies are pipelined with the per-column sorts (page-locked host memory makes them asynchronous). */
+PBL_API int pbl_ic_plan_run_host(pbl_ic_plan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
+                                 double* Y, int64_t y_row_stride, int64_t y_col_stride, double* X_staging_dev,
+                                 double* Y_staging_dev, void* stream);
+
 /* Same call with HOST buffers (what a NumPy caller holds): copies X to the device, runs, copies Y
  * back.  X and Y must each be one contiguous block in C or F order. */
 PBL_API int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t x_row_stride,

@@ -190,6 +190,7 @@ class _PlanCorrelator(Correlator):
     device entry points, status -> exception mapping."""
 
     _entry = None        # C symbol that runs the transform on a plan
+    _entry_host = None   # C symbol with host buffers and pipelined copies (optional)
     _rows_only = False   # plan without sort workspace
 
     def __init__(self, device=None, col_batch=0):
@@ -278,10 +279,16 @@ class _PlanCorrelator(Correlator):
         dX, dY, _ = self._dev_bufs
         rs, cs = _strides_elems(Xd.shape, Xd.strides, 8)
         yrs, ycs = _strides_elems(result.shape, result.strides, 8)
-        _lib.check(lib.pbl_memcpy_h2d(dX, Xd.ctypes.data, nbytes, None), "pbl_memcpy_h2d")
-        self._run(plan, dX, rs, cs, dY, yrs, ycs, None)
-        _lib.check(lib.pbl_memcpy_d2h(result.ctypes.data, dY, nbytes, None), "pbl_memcpy_d2h")
-        _lib.check(lib.pbl_stream_synchronize(None), "pbl_stream_synchronize")
+        if self._entry_host is not None:
+            fn = getattr(lib, self._entry_host)
+            st = _lib.check(fn(plan.handle, Xd.ctypes.data, rs, cs, result.ctypes.data, yrs, ycs,
+                               C.c_void_p(dX), C.c_void_p(dY), None), self._entry_host)
+            self._raise(st)
+        else:
+            _lib.check(lib.pbl_memcpy_h2d(dX, Xd.ctypes.data, nbytes, None), "pbl_memcpy_h2d")
+            self._run(plan, dX, rs, cs, dY, yrs, ycs, None)
+            _lib.check(lib.pbl_memcpy_d2h(result.ctypes.data, dY, nbytes, None), "pbl_memcpy_d2h")
+            _lib.check(lib.pbl_stream_synchronize(None), "pbl_stream_synchronize")
         if result.dtype != X.dtype and self._keeps_dtype:
             result = result.astype(X.dtype)  # np.empty_like(X) keeps X's dtype in the reference
         return result
@@ -327,6 +334,7 @@ class ImanConover(_PlanCorrelator):
     """
 
     _entry = "pbl_ic_plan_run"
+    _entry_host = "pbl_ic_plan_run_host"
     _keeps_dtype = True
 
 

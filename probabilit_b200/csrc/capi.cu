@@ -146,6 +146,22 @@ static bool contiguous_layout(int64_t n, int32_t k, int64_t rs, int64_t cs) {
   return (rs == 1 && cs == n) || (cs == 1 && rs == k) || (n == 1 && cs == 1) || (k == 1 && rs == 1);
 }
 
+int pbl_ic_plan_run_host(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, double* Y, int64_t yrs,
+                         int64_t ycs, double* X_staging_dev, double* Y_staging_dev, void* stream) {
+  if (!plan || !X || !Y || !X_staging_dev || !Y_staging_dev) return kBadShape;
+  if (!plan->impl->has_target) {
+    pbl::set_last_error("User must call `set_target` first.");
+    return kBadShape;
+  }
+  if (!contiguous_layout(plan->impl->n, plan->impl->k, xrs, xcs) ||
+      !contiguous_layout(plan->impl->n, plan->impl->k, yrs, ycs)) {
+    pbl::set_last_error("pbl_ic_plan_run_host: X and Y must be contiguous in C or F order");
+    return kBadShape;
+  }
+  return pbl::ic_plan_run_host(plan->impl, X, xrs, xcs, Y, yrs, ycs, X_staging_dev, Y_staging_dev,
+                               (cudaStream_t)stream);
+}
+
 int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t xrs, int64_t xcs,
                          const double* P_lower, double* Y, int64_t yrs, int64_t ycs) {
   if (!X || !Y || !P_lower) return kBadShape;
@@ -161,9 +177,7 @@ int pbl_iman_conover_f64(const double* X, int64_t n, int32_t k, int64_t xrs, int
   if (rc == kOk && cudaMalloc((void**)&dX, bytes) != cudaSuccess) rc = pbl::kCudaError;
   if (rc == kOk && cudaMalloc((void**)&dY, bytes) != cudaSuccess) rc = pbl::kCudaError;
   if (rc == pbl::kCudaError && !*pbl::get_last_error()) pbl::set_last_error("cudaMalloc failed");
-  if (rc == kOk && cudaMemcpy(dX, X, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = pbl::kCudaError;
-  if (rc == kOk) rc = pbl_ic_plan_run(plan, dX, xrs, xcs, dY, yrs, ycs, nullptr);
-  if (rc == kOk && cudaMemcpy(Y, dY, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = pbl::kCudaError;
+  if (rc == kOk) rc = pbl_ic_plan_run_host(plan, X, xrs, xcs, Y, yrs, ycs, dX, dY, nullptr);
   cudaFree(dX);
   cudaFree(dY);
   pbl_ic_plan_destroy(plan);

@@ -761,6 +761,8 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->gram_partials);
   cudaFree(p->moments);
   permcorr_free(p->permcorr);
+  for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   delete p;
 }
 
@@ -945,6 +947,64 @@ int cholesky_correlator_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs
     return kNotPositiveDefinite;
   }
   return kOk;
+}
+
+// ImanConover.__call__ with HOST buffers, pipelined: the host->device copy of column batch b+1
+// overlaps the rank_scores sorts of batch b, and the device->host copy of batch b overlaps the
+// rank_gather sorts of batch b+1 (columns are independent in both sort stages; only the Gram /
+// solve / transform in the middle need every column).  dX / dY: device staging of n*k doubles each.
+int ic_plan_run_host(IcPlan* p, const double* Xh, int64_t xrs, int64_t xcs, double* Yh, int64_t yrs,
+                     int64_t ycs, double* dX, double* dY, cudaStream_t stream) {
+  const int64_t n = p->n;
+  const int k = p->k;
+  const size_t bytes = (size_t)n * k * 8;
+  const bool colmajor = (xrs == 1 && xcs == n && yrs == 1 && ycs == n) || k == 1;
+  if (!colmajor) {  // C order: one block each way, no overlap
+    PBL_CUDA_CHECK(cudaMemcpyAsync(dX, Xh, bytes, cudaMemcpyHostToDevice, stream));
+    int st = ic_plan_run(p, dX, xrs, xcs, dY, yrs, ycs, stream);
+    if (st != kOk) return st;
+    PBL_CUDA_CHECK(cudaMemcpyAsync(Yh, dY, bytes, cudaMemcpyDeviceToHost, stream));
+    PBL_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return kOk;
+  }
+  if (!p->copy_stream) {
+    PBL_CUDA_CHECK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  }
+  const int bc = std::max(1, std::min(p->col_batch, k >= 8 ? 2 : 1));  // columns per pipeline stage
+  const int nb = (k + bc - 1) / bc;
+  while ((int)p->events.size() < 2 * nb) {
+    cudaEvent_t e;
+    PBL_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->events.push_back(e);
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
+    // the copy stream must not run ahead of work queued earlier on `stream` (e.g. a previous call's D2H)
+    for (int b = 0; b < nb; ++b) {
+      const int c0 = b * bc, nc = std::min(bc, k - c0);
+      PBL_CUDA_CHECK(cudaMemcpyAsync(dX + (size_t)c0 * n, Xh + (size_t)c0 * n, (size_t)nc * n * 8,
+                                     cudaMemcpyHostToDevice, p->copy_stream));
+      PBL_CUDA_CHECK(cudaEventRecord(p->events[b], p->copy_stream));
+      PBL_CUDA_CHECK(cudaStreamWaitEvent(stream, p->events[b], 0));
+      PBL_RETURN_IF(ic_stage_rank_scores(p, dX, 1, n, c0, nc, stream));
+    }
+    PBL_RETURN_IF(ic_stage_gram(p, stream));
+    PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
+    PBL_RETURN_IF(ic_stage_transform(p, stream));
+    for (int b = 0; b < nb; ++b) {
+      const int c0 = b * bc, nc = std::min(bc, k - c0);
+      PBL_RETURN_IF(ic_stage_rank_gather(p, dY, 1, n, c0, nc, stream));
+      PBL_CUDA_CHECK(cudaEventRecord(p->events[nb + b], stream));
+      PBL_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->events[nb + b], 0));
+      PBL_CUDA_CHECK(cudaMemcpyAsync(Yh + (size_t)c0 * n, dY + (size_t)c0 * n, (size_t)nc * n * 8,
+                                     cudaMemcpyDeviceToHost, p->copy_stream));
+    }
+    int st = ic_read_status(p, stream);
+    PBL_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
+    if (st != kRetry) return st;
+  }
+  set_last_error("windowed sort retry did not converge (internal error)");
+  return kInternal;
 }
 
 // Column means (MODE 0) or population standard deviations about `mean` (MODE 1) of an (n, k) matrix,

@@ -1,6 +1,8 @@
 // Iman-Conover on the device: plan object + stage entry points (internal C++ API; the C ABI
 // in capi.cu is a thin wrapper).  Reference: src/probabilit/correlation.py:368-425.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -30,6 +32,8 @@ struct IcPlan {
   double* T = nullptr;         // [k][k] row-major, upper triangular: correlated = scores @ T
   double* P = nullptr;         // [k][k] row-major lower Cholesky factor of the target C
   double* moments = nullptr;   // Cholesky correlator: [k] mean, [k] std, [k][256] partial sums (lazy)
+  cudaStream_t copy_stream = nullptr;   // host-buffer entry point: copies overlap the sorts
+  std::vector<cudaEvent_t> events;
   void* permcorr = nullptr;    // PermutationCorrelator state (permcorr.cu), lazy
   uint32_t* flags = nullptr;   // [8], see SortFlag in sort.cuh
   size_t bytes = 0;            // device bytes held by the plan
@@ -45,6 +49,11 @@ int ic_plan_set_target(IcPlan* plan, const double* P_lower_host);
 // call is synchronous and the status has to come back).
 int ic_plan_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
                 double* Y, int64_t y_row_stride, int64_t y_col_stride, cudaStream_t stream);
+
+// Same with HOST buffers (column-major or C order), copies inside and overlapped with the sorts.
+int ic_plan_run_host(IcPlan* plan, const double* X_host, int64_t x_row_stride, int64_t x_col_stride,
+                     double* Y_host, int64_t y_row_stride, int64_t y_col_stride, double* dX, double* dY,
+                     cudaStream_t stream);
 
 // Stage-level entry points (parity tests, and the multi-GPU host driver which interleaves
 // collectives between them).  All asynchronous on `stream`.
