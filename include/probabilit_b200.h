@@ -30,7 +30,7 @@ typedef enum pbl_status {
   PBL_BAD_SHAPE = 3,             /* ValueError from Correlator._validate_X, correlation.py:181-202 */
   PBL_CUDA_ERROR = 4,
   PBL_INTERNAL = 5,
-  PBL_RETRY = 6 /* stage API only (pbl_ic_stage_status): the data are too dense for the 40-bit sort window;
+  PBL_RETRY = 6 /* stage API only (pbl_ic_stage_status): the data are too dense for the 32-bit sort window;
                    the plan has switched to the exact 64-bit sort, repeat from pbl_ic_stage_begin.
                    pbl_ic_plan_run / pbl_iman_conover_f64 handle this internally. */
 } pbl_status;

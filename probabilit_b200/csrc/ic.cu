@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kPostBlock)
 post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB,
                  const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
                  int window_bits, uint32_t n, double* __restrict__ sortedX,
-                 const double* __restrict__ vdw, uint32_t* __restrict__ flags) {
+                 const double* __restrict__ vdw, uint32_t* __restrict__ flags, int col_base) {
   extern __shared__ __align__(16) unsigned char psm[];
   uint64_t* s_raw = reinterpret_cast<uint64_t*>(psm);        // [kWin] keys as the sort left them
   uint64_t* s_key = s_raw + kWin;                            // [kWin] completed order
@@ -277,7 +277,8 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
           sc = ndtri(__ddiv_rn(avg, (double)((uint64_t)n + 1ull)));
         }
         stage[g] = sc;
-        sx[g] = (row & kNegZeroFlag) ? -0.0 : key_to_double(s_key[kHalo + p]);
+        sx[g] = (row & kNegZeroFlag) ? -0.0 : key_to_double(expand_key(s_key[kHalo + p], map));
+        if ((row & kNegZeroFlag) && col + col_base == 0) flags[kFlagNegZeroCol0] = 1u;
       } else {
         uint32_t m = s + (e - s) / 2;
         stage[g] = sx[m];
@@ -681,7 +682,7 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
   const char* lb = getenv("PBL_SORT_LOOKBACK");
   p->use_lookback = !(lb && lb[0] == '0');
   const char* wb = getenv("PBL_WINDOW_BITS");
-  p->window_bits = (wb && atoi(wb) == 64) ? 64 : 40;
+  p->window_bits = (wb && atoi(wb) == 64) ? 64 : 32;
 
   // column batch: as many columns per launch as fit in ~45% of free memory
   size_t free_b = 0, total_b = 0;
@@ -708,7 +709,7 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
     A(&p->sort.hist, (size_t)cb * kMaxPasses * kRadix);
     A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
     A(&p->sort.tile_counter, (size_t)cb * (kMaxPasses + 1));
-    A(&p->sort.kminmax, (size_t)cb * 2);
+    A(&p->sort.kminmax, (size_t)cb * kMinMaxWords);
     A(&p->sort.plan, (size_t)cb);
     A(&p->sortedX, (size_t)k * n);
     A(&p->vdw, (size_t)n);
@@ -809,11 +810,11 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     if (ranks_only)
       post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
     else
       post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
                                  p->use_lookback, stream));
@@ -893,7 +894,7 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_RETURN_IF(post_sort_attr());
     post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
         p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags);
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
                                  col_stride, p->use_lookback, stream));
@@ -949,6 +950,31 @@ int cholesky_correlator_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs
   return kOk;
 }
 
+__global__ void __launch_bounds__(256)
+copy_column_kernel(const double* __restrict__ X, int64_t xrs, double* __restrict__ Y, int64_t yrs, int64_t n) {
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
+    Y[r * yrs] = ld_stream_f64(X + r * xrs);
+}
+
+// Column 0 needs no second sort when T[0][0] == 1 exactly: its correlated score is then the van der
+// Waerden score itself (T is upper triangular), whose order and tie-runs are those of X[:, 0], so
+// the reference's gather returns X[:, 0] unchanged (every member of a tie-run receives the run's
+// common value).  Only a column holding both zeros is excluded (its tie-run mixes -0.0 and +0.0).
+// Returns the first column that still has to be ranked (0 or 1); Y[:, 0] <- X[:, 0] when skipped.
+static int first_column_to_rank(IcPlan* p, const double* X, int64_t xrs, double* Y, int64_t yrs,
+                                cudaStream_t stream) {
+  double t00 = 0.0;
+  uint32_t h[8];
+  if (cudaMemcpyAsync(&t00, p->T, sizeof(double), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 0;
+  if (cudaMemcpyAsync(h, p->flags, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 0;
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return 0;
+  if (t00 != 1.0 || h[kFlagNegZeroCol0] || h[kFlagNotPD] || h[kFlagNaN] || h[kFlagWindowRetry]) return 0;
+  const unsigned rb = (unsigned)std::min<int64_t>((p->n + 255) / 256, (int64_t)num_sms() * 16);
+  copy_column_kernel<<<rb, 256, 0, stream>>>(X, xrs, Y, yrs, p->n);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return 1;
+}
+
 // ImanConover.__call__ with HOST buffers, pipelined: the host->device copy of column batch b+1
 // overlaps the rank_scores sorts of batch b, and the device->host copy of batch b overlaps the
 // rank_gather sorts of batch b+1 (columns are independent in both sort stages; only the Gram /
@@ -991,9 +1017,11 @@ int ic_plan_run_host(IcPlan* p, const double* Xh, int64_t xrs, int64_t xcs, doub
     PBL_RETURN_IF(ic_stage_gram(p, stream));
     PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
     PBL_RETURN_IF(ic_stage_transform(p, stream));
+    const int skip0 = first_column_to_rank(p, dX, 1, dY, 1, stream);
     for (int b = 0; b < nb; ++b) {
       const int c0 = b * bc, nc = std::min(bc, k - c0);
-      PBL_RETURN_IF(ic_stage_rank_gather(p, dY, 1, n, c0, nc, stream));
+      const int r0 = std::max(c0, skip0);
+      if (r0 < c0 + nc) PBL_RETURN_IF(ic_stage_rank_gather(p, dY, 1, n, r0, c0 + nc - r0, stream));
       PBL_CUDA_CHECK(cudaEventRecord(p->events[nb + b], stream));
       PBL_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->events[nb + b], 0));
       PBL_CUDA_CHECK(cudaMemcpyAsync(Yh + (size_t)c0 * n, dY + (size_t)c0 * n, (size_t)nc * n * 8,
@@ -1063,7 +1091,7 @@ int ic_read_status(IcPlan* p, cudaStream_t stream) {
     return kNonFinite;
   }
   if (h[kFlagWindowRetry] && p->window_bits < 64) {
-    // the data are too dense for the 40-bit window: from now on this plan sorts on all 64 bits
+    // the data are too dense for the 32-bit window: from now on this plan sorts on all 64 bits
     p->window_bits = 64;
     set_last_error("windowed sort could not be completed; repeat the call (full 64-bit sort)");
     return kRetry;
@@ -1083,7 +1111,8 @@ int ic_plan_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, double* Y,
     PBL_RETURN_IF(ic_stage_gram(p, stream));
     PBL_RETURN_IF(ic_stage_solve(p, p->n, stream));
     PBL_RETURN_IF(ic_stage_transform(p, stream));
-    PBL_RETURN_IF(ic_stage_rank_gather(p, Y, yrs, ycs, 0, p->k, stream));
+    const int c0 = first_column_to_rank(p, X, xrs, Y, yrs, stream);
+    if (c0 < p->k) PBL_RETURN_IF(ic_stage_rank_gather(p, Y, yrs, ycs, c0, p->k - c0, stream));
     int st = ic_read_status(p, stream);
     if (st != kRetry) return st;
   }

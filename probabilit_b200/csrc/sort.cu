@@ -27,8 +27,10 @@ __device__ __forceinline__ uint64_t key_of_double(double d, bool* neg_zero) {
 __global__ void minmax_init_kernel(uint64_t* __restrict__ kminmax, int ncols) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < ncols) {
-    kminmax[2 * c] = ~0ull;
-    kminmax[2 * c + 1] = 0ull;
+    kminmax[kMinMaxWords * c] = ~0ull;
+    kminmax[kMinMaxWords * c + 1] = 0ull;
+    kminmax[kMinMaxWords * c + 2] = 0ull;   // largest key below the zero key
+    kminmax[kMinMaxWords * c + 3] = ~0ull;  // smallest key above the zero key
   }
 }
 
@@ -36,10 +38,13 @@ template <int BLOCK, int UNROLL>
 __global__ void __launch_bounds__(BLOCK)
 col_minmax_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride, uint32_t n,
                   uint64_t* __restrict__ kminmax, uint32_t* __restrict__ error_flag) {
-  __shared__ uint64_t s_lo[BLOCK / 32], s_hi[BLOCK / 32];
+  // tracked as doubles (one fmin / fmax each; 64-bit integer min/max cost ~5 ALU instructions on a
+  // part whose integer pipe is the bottleneck) and converted to keys once per block
+  __shared__ double s_lo[BLOCK / 32], s_hi[BLOCK / 32], s_nm[BLOCK / 32], s_pm[BLOCK / 32];
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
   const int col = blockIdx.y;
   const double* colp = raw + (int64_t)col * col_stride;
-  uint64_t lo = ~0ull, hi = 0ull;
+  double lo = inf, hi = -inf, negmax = -inf, posmin = inf;  // fmin / fmax drop NaNs
   bool saw_nan = false;
   const uint64_t step = (uint64_t)gridDim.x * BLOCK * UNROLL;
   for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n; base += step) {
@@ -51,39 +56,51 @@ col_minmax_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t co
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      bool nz;
-      uint64_t k = key_of_double(d[u], &nz);
       saw_nan |= (d[u] != d[u]);
-      lo = min(lo, k);
-      hi = max(hi, k);
+      lo = fmin(lo, d[u]);
+      hi = fmax(hi, d[u]);
+      negmax = fmax(negmax, d[u] < 0.0 ? d[u] : -inf);
+      posmin = fmin(posmin, d[u] > 0.0 ? d[u] : inf);
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    negmax = fmax(negmax, __shfl_xor_sync(0xFFFFFFFFu, negmax, o));
+    posmin = fmin(posmin, __shfl_xor_sync(0xFFFFFFFFu, posmin, o));
   }
   if ((threadIdx.x & 31) == 0) {
     s_lo[threadIdx.x >> 5] = lo;
     s_hi[threadIdx.x >> 5] = hi;
+    s_nm[threadIdx.x >> 5] = negmax;
+    s_pm[threadIdx.x >> 5] = posmin;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < BLOCK / 32; ++w) {
-      lo = min(lo, s_lo[w]);
-      hi = max(hi, s_hi[w]);
+      lo = fmin(lo, s_lo[w]);
+      hi = fmax(hi, s_hi[w]);
+      negmax = fmax(negmax, s_nm[w]);
+      posmin = fmin(posmin, s_pm[w]);
     }
-    atomicMin((unsigned long long*)&kminmax[2 * col], (unsigned long long)lo);
-    atomicMax((unsigned long long*)&kminmax[2 * col + 1], (unsigned long long)hi);
+    if (lo <= hi) {  // at least one non-NaN value seen
+      bool nz;
+      unsigned long long* q = (unsigned long long*)&kminmax[kMinMaxWords * col];
+      atomicMin(q, (unsigned long long)key_of_double(lo, &nz));
+      atomicMax(q + 1, (unsigned long long)key_of_double(hi, &nz));
+      if (lo < 0.0) atomicMax(q + 2, (unsigned long long)key_of_double(negmax, &nz));
+      if (hi > 0.0) atomicMin(q + 3, (unsigned long long)key_of_double(posmin, &nz));
+    }
   }
   if (saw_nan) error_flag[kFlagNaN] = 1u;
 }
 
 // --------------------------------------------------------------------------------------
 // Kernel 1: the digit histograms of every column's window values in one read of the input
-// (8 B / key).  Shared-memory atomics; the most significant digit (few distinct values for real
-// data, i.e. same-address conflicts) is warp-aggregated with match.any, which is cheap exactly
-// when few distinct values are present.
+// (8 B / key).  Plain shared-memory reductions: with the compact window every digit, including
+// the most significant one, is spread over many values, so same-address conflicts are rare and
+// warp aggregation (MATCH.ANY, ~2 cycles per distinct value per SM) would cost more than it saves.
 // --------------------------------------------------------------------------------------
 template <int BLOCK, int UNROLL, int NP>
 __global__ void __launch_bounds__(BLOCK)
@@ -95,29 +112,29 @@ sort_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col
   const int col = blockIdx.y;
   const KeyMap map = load_key_map(kminmax, col, window_bits);
   const double* colp = raw + (int64_t)col * col_stride;
-  const uint32_t lane = lane_id();
+  const uint32_t sh_addr = (uint32_t)__cvta_generic_to_shared(&sh[0][0]);
   const uint64_t step = (uint64_t)gridDim.x * BLOCK * UNROLL;
-  // the loop bound is warp-uniform so that match.any sees the full warp
   for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n; base += step) {
-    uint64_t w[UNROLL];
+    double d[UNROLL];
     bool valid[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       uint64_t i = base + (uint64_t)u * BLOCK + threadIdx.x;
       valid[u] = i < n;
-      double d = valid[u] ? ld_stream_f64(colp + (int64_t)i * row_stride) : 0.0;
-      bool nz;
-      w[u] = window_value(key_of_double(d, &nz), map);
+      d[u] = valid[u] ? ld_stream_f64(colp + (int64_t)i * row_stride) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
+      bool nz;
+      const uint64_t w = window_value(compact_key(key_of_double(d[u], &nz), map), map);
       if (valid[u]) {
 #pragma unroll
-        for (int p = 0; p < NP - 1; ++p) atomicAdd(&sh[p][(uint32_t)(w[u] >> (8 * p)) & 255u], 1u);
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t dg = (uint32_t)(w >> (8 * p)) & 255u;
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sh_addr + (uint32_t)(p * kRadix + dg) * 4u), "r"(1u)
+                       : "memory");
+        }
       }
-      uint32_t top = valid[u] ? (uint32_t)(w[u] >> (8 * (NP - 1))) & 0xFFu : 0xFFFFFFFFu;
-      uint32_t m = __match_any_sync(0xFFFFFFFFu, top);
-      if (valid[u] && lane == (uint32_t)(__ffs(m) - 1)) atomicAdd(&sh[NP - 1][top], (uint32_t)__popc(m));
     }
   }
   __syncthreads();
@@ -207,7 +224,7 @@ tile_hist_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col
     uint64_t k;
     if (src == 0) {
       bool nz;
-      k = key_of_double(raw[(int64_t)col * col_stride + (int64_t)(start + pos) * row_stride], &nz);
+      k = compact_key(key_of_double(raw[(int64_t)col * col_stride + (int64_t)(start + pos) * row_stride], &nz), map);
     } else {
       k = (src == 1 ? keysA : keysB)[(size_t)col * n + start + pos];
     }
@@ -236,15 +253,23 @@ __global__ void tile_scan_kernel(uint32_t* __restrict__ tile_counts,
 // so that (warp, item, lane) order == position order (every LSD pass must be stable).
 //   load -> early per-warp digit counts -> tile counts published for the tiles behind us
 //   -> ballot-based ranking, one shared-memory atomic per distinct digit and warp
-//   -> scatter key+payload into shared memory in digit order -> look back for the exclusive
-//   tile prefix per bin -> coalesced runs out to HBM.
-// SCATTER = false: radix digit pass of the sort  (key u64 = fp64 image, payload u32 = row).
+//   -> scatter key + payload + digit byte into shared memory in digit order -> look back for the
+//   exclusive tile prefix per bin -> coalesced runs out to HBM.
+// SCATTER = false: radix digit pass of the sort  (key u64 = compact key, payload u32 = row).
 // SCATTER = true : first half of the "scatter by row" step that follows each sort: key u32 =
 //   destination row, payload u64 = the fp64 value to deliver; digit = row >> shift, i.e. the
 //   elements are grouped into <= 256 destination windows small enough to live in L2, so that
 //   the second half (scatter_rows_kernel) writes every 128 B line of the output exactly once
 //   from L2 instead of issuing 1e8 random 8 B read-modify-writes to HBM.  Rows are a
 //   permutation, so the bin bases are known without a histogram.
+//
+// The kernel is bound by the integer ALU pipe on B200 (ncu: issue ~50 %, alu pipe saturated; a
+// B200 has about half the integer issue rate per byte of HBM bandwidth of an H100), so the code
+// is organised to minimise ALU instructions per key:
+//   * keys are stored COMPACT (sort.cuh): the digit is one 64-bit shift + mask;
+//   * the digit is computed once and travels through shared memory as a byte;
+//   * full tiles (all but the last tile of a column) run a path without any bounds predicate;
+//   * global addresses are formed with mad.wide (fma pipe) instead of shift/add pairs.
 // --------------------------------------------------------------------------------------
 template <bool SCATTER> struct PassTypes { using Key = uint64_t; using Val = uint32_t; };
 template <> struct PassTypes<true> { using Key = uint32_t; using Val = uint64_t; };
@@ -260,7 +285,7 @@ struct PassArgs {
   uint32_t* status;              // [ncols][ntiles][256] look-back words (or tile offsets)
   uint32_t* tile_counter;        // [ncols]
   const PassPlan* plan;
-  const uint64_t* kminmax;       // SORT: [ncols][2]
+  const uint64_t* kminmax;       // SORT: [ncols][4]
   uint32_t* error_flag;
   uint32_t n;
   int pass;                      // SORT: digit index;  SCATTER: unused
@@ -270,96 +295,87 @@ struct PassArgs {
   int use_lookback;
 };
 
-template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
-__global__ void __launch_bounds__(BLOCK, MINB)
-partition_pass_kernel(const PassArgs a) {
+__device__ __forceinline__ void st_u64_at(uint64_t* base, uint32_t idx, uint64_t v) {
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+  *reinterpret_cast<uint64_t*>(addr) = v;
+}
+__device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t v) {
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+  *reinterpret_cast<uint32_t*>(addr) = v;
+}
+
+struct PassSmem {
+  uint64_t* big;      // [TILE] 8-byte member
+  uint32_t* small_;   // [TILE] 4-byte member
+  uint8_t* dig;       // [TILE] digit of the element at each tile-local (digit-ordered) position
+  uint32_t* hist;     // [NWARPS][kRadix]
+  uint32_t* goff;     // [kRadix] global slot - tile position
+  uint32_t* bstart;   // [kRadix] tile-local bin start
+  uint32_t* wsum;     // [8]
+};
+
+template <int BLOCK, int ITEMS, bool SCATTER, bool FULL>
+__device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm, const int col,
+                                          const uint32_t tile, const uint32_t nvalid, const int src,
+                                          const int dst, const uint32_t dshift, const KeyMap& map) {
   using Key = typename PassTypes<SCATTER>::Key;
   using Val = typename PassTypes<SCATTER>::Val;
   constexpr int TILE = BLOCK * ITEMS;
   constexpr int NWARPS = BLOCK / 32;
-  static_assert(BLOCK >= kRadix && BLOCK % 32 == 0, "one thread per bin is assumed");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* s_big = reinterpret_cast<uint64_t*>(smem_raw);             // [TILE] 8-byte member
-  uint32_t* s_small = reinterpret_cast<uint32_t*>(s_big + TILE);       // [TILE] 4-byte member
-  uint32_t* s_hist = s_small + TILE;                                   // [NWARPS][kRadix]
-  uint32_t* s_goff = s_hist + NWARPS * kRadix;                         // [kRadix] global slot - tile position
-  uint32_t* s_bstart = s_goff + kRadix;                                // [kRadix] tile-local bin start
-  uint32_t* s_wsum = s_bstart + kRadix;                                // [8]
-  uint32_t* s_tile = s_wsum + 8;                                       // [1]
-  Key* s_keys = SCATTER ? reinterpret_cast<Key*>(s_small) : reinterpret_cast<Key*>(s_big);
-  Val* s_vals = SCATTER ? reinterpret_cast<Val*>(s_big) : reinterpret_cast<Val*>(s_small);
-
-  const int col = blockIdx.y;
+  Key* s_keys = SCATTER ? reinterpret_cast<Key*>(sm.small_) : reinterpret_cast<Key*>(sm.big);
+  Val* s_vals = SCATTER ? reinterpret_cast<Val*>(sm.big) : reinterpret_cast<Val*>(sm.small_);
   const int tid = threadIdx.x;
   const uint32_t n = a.n;
-  // SORT:    reads (keys, rows)[src] (or the raw column), writes (keys, rows)[dst]
-  // SCATTER: reads rows + staged values from buffer "other", writes rows + values to "final"
-  int src, dst;
-  uint32_t tsh;
-  uint64_t kmin = 0;
-  if (SCATTER) {
-    dst = a.plan[col].final_buf;
-    src = (dst == 1) ? 2 : 1;
-    tsh = (uint32_t)a.shift;
-  } else {
-    if (!a.plan[col].run[a.pass]) return;
-    src = a.plan[col].src[a.pass];
-    dst = (src == 1) ? 2 : 1;
-    const KeyMap map = load_key_map(a.kminmax, col, a.window_bits);
-    kmin = map.kmin;
-    tsh = map.sh + (uint32_t)a.pass * kRadixBits;
-  }
-  auto digit = [&](Key k) -> uint32_t {
-    return SCATTER ? (uint32_t)((uint32_t)k >> tsh)
-                   : ((uint32_t)(((uint64_t)k - kmin) >> tsh) & (uint32_t)(kRadix - 1));
-  };
-
-  if (tid == 0) *s_tile = atomicAdd(&a.tile_counter[col], 1u);
-  for (int i = tid; i < NWARPS * kRadix; i += BLOCK) s_hist[i] = 0;
-  __syncthreads();
-  const uint32_t tile = *s_tile;
   const uint32_t tile_start = tile * (uint32_t)TILE;
-  const uint32_t nvalid = min((uint32_t)TILE, n - tile_start);
   const uint32_t warp = tid >> 5, lane = tid & 31;
   const uint32_t pos0 = warp * (ITEMS * 32) + lane;
 
-  // ---- load keys; padding (positions >= nvalid) is forced into the last bin, where it sorts
-  //      after every real key of the tile because it also has the highest positions ----
+  // ---- load keys and take their digits; padding (positions >= nvalid, partial tiles only) is
+  //      forced into the last bin, where it sorts after every real key of the tile because it
+  //      also has the highest positions ----
   Key key[ITEMS];
+  uint32_t dig[ITEMS];
   uint32_t negzero = 0;  // SORT from raw: bit u set if item u was -0.0
   if (SCATTER) {
-    const uint32_t* kin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
+    const uint32_t* kin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start + pos0;
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) {
-      uint32_t pos = pos0 + u * 32;
-      key[u] = (pos < nvalid) ? (Key)ld_stream_u32(kin + pos) : (Key)0;
-    }
+    for (int u = 0; u < ITEMS; ++u)
+      key[u] = (FULL || pos0 + u * 32 < nvalid) ? (Key)ld_stream_u32(kin + u * 32) : (Key)0;
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) dig[u] = (uint32_t)key[u] >> dshift;
   } else if (src == 0) {
-    const double* colp = a.raw + (int64_t)col * a.col_stride + (int64_t)tile_start * a.row_stride;
+    const double* colp = a.raw + (int64_t)col * a.col_stride + (int64_t)(tile_start + pos0) * a.row_stride;
+    const int64_t step = 32 * a.row_stride;
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
-      uint32_t pos = pos0 + u * 32;
       key[u] = (Key)0;
-      if (pos < nvalid) {
+      if (FULL || pos0 + u * 32 < nvalid) {
         bool nz;
-        key[u] = (Key)key_of_double(ld_stream_f64(colp + (int64_t)pos * a.row_stride), &nz);
+        const uint64_t k = key_of_double(ld_stream_f64(colp + u * step), &nz);
+        key[u] = (Key)compact_key(k, map);
         negzero |= (nz ? 1u : 0u) << u;
       }
     }
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) dig[u] = (uint32_t)((uint64_t)key[u] >> dshift) & (uint32_t)(kRadix - 1);
   } else {
-    const uint64_t* kin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
+    const uint64_t* kin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start + pos0;
 #pragma unroll
-    for (int u = 0; u < ITEMS; ++u) {
-      uint32_t pos = pos0 + u * 32;
-      key[u] = (pos < nvalid) ? (Key)ld_stream_u64(kin + pos) : (Key)0;
-    }
+    for (int u = 0; u < ITEMS; ++u)
+      key[u] = (FULL || pos0 + u * 32 < nvalid) ? (Key)ld_stream_u64(kin + u * 32) : (Key)0;
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) dig[u] = (uint32_t)((uint64_t)key[u] >> dshift) & (uint32_t)(kRadix - 1);
   }
-  uint32_t dig[ITEMS];  // 8-bit digits, packed 4 per register by the compiler's choice
+  if (!FULL) {
 #pragma unroll
-  for (int u = 0; u < ITEMS; ++u) dig[u] = (pos0 + u * 32 < nvalid) ? digit(key[u]) : (uint32_t)(kRadix - 1);
+    for (int u = 0; u < ITEMS; ++u)
+      if (pos0 + u * 32 >= nvalid) dig[u] = (uint32_t)(kRadix - 1);
+  }
 
   // ---- early counts: warp-private digit histograms (fire-and-forget shared atomics) ----
-  uint32_t* wh = s_hist + warp * kRadix;
+  uint32_t* wh = sm.hist + warp * kRadix;
   const uint32_t wh_addr = (uint32_t)__cvta_generic_to_shared(wh);
 #pragma unroll
   for (int u = 0; u < ITEMS; ++u) {
@@ -376,10 +392,10 @@ partition_pass_kernel(const PassArgs a) {
   if (tid < kRadix) {
     uint32_t wc[NWARPS];
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) wc[w] = s_hist[w * kRadix + tid];
+    for (int w = 0; w < NWARPS; ++w) wc[w] = sm.hist[w * kRadix + tid];
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) cnt += wc[w];
-    if (tid == kRadix - 1) cnt -= (uint32_t)TILE - nvalid;  // drop the padding keys
+    if (!FULL && tid == kRadix - 1) cnt -= (uint32_t)TILE - nvalid;  // drop the padding keys
     if (a.use_lookback)
       st_relaxed_u32(&st[(size_t)tile * kRadix + tid], cnt | (tile == 0 ? kFlagInclusive : kFlagPartial));
     uint32_t incl = cnt;
@@ -388,14 +404,14 @@ partition_pass_kernel(const PassArgs a) {
       uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
-    if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 31) sm.wsum[warp] = incl;
     bin_start = incl - cnt;
     // warp-private counters become running offsets *within the bin* (the bin start is added
     // below, once the scan over bins is complete)
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
-      s_hist[w * kRadix + tid] = run;
+      sm.hist[w * kRadix + tid] = run;
       run += wc[w];
     }
   }
@@ -403,8 +419,8 @@ partition_pass_kernel(const PassArgs a) {
   if (tid < kRadix) {
 #pragma unroll
     for (int w = 0; w < kRadix / 32; ++w)
-      if ((uint32_t)w < warp) bin_start += s_wsum[w];
-    s_bstart[tid] = bin_start;
+      if ((uint32_t)w < warp) bin_start += sm.wsum[w];
+    sm.bstart[tid] = bin_start;
   }
 
   // ---- rank inside the warp.  Three phases so that the ITEMS chains overlap instead of
@@ -450,8 +466,9 @@ partition_pass_kernel(const PassArgs a) {
   // ---- scatter to shared memory in digit order ----
 #pragma unroll
   for (int u = 0; u < ITEMS; ++u) {
-    rank[u] += s_bstart[dig[u]];
+    rank[u] += sm.bstart[dig[u]];
     s_keys[rank[u]] = key[u];
+    sm.dig[rank[u]] = (uint8_t)dig[u];
   }
   if (!SCATTER && src == 0) {
 #pragma unroll
@@ -460,19 +477,15 @@ partition_pass_kernel(const PassArgs a) {
   } else {
     Val v[ITEMS];
     if (SCATTER) {
-      const uint64_t* vin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start;
+      const uint64_t* vin = (src == 1 ? a.keysA : a.keysB) + (size_t)col * n + tile_start + pos0;
 #pragma unroll
-      for (int u = 0; u < ITEMS; ++u) {
-        uint32_t pos = pos0 + u * 32;
-        v[u] = (pos < nvalid) ? (Val)ld_stream_u64(vin + pos) : (Val)0;
-      }
+      for (int u = 0; u < ITEMS; ++u)
+        v[u] = (FULL || pos0 + u * 32 < nvalid) ? (Val)ld_stream_u64(vin + u * 32) : (Val)0;
     } else {
-      const uint32_t* vin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start;
+      const uint32_t* vin = (src == 1 ? a.valsA : a.valsB) + (size_t)col * n + tile_start + pos0;
 #pragma unroll
-      for (int u = 0; u < ITEMS; ++u) {
-        uint32_t pos = pos0 + u * 32;
-        v[u] = (pos < nvalid) ? (Val)ld_stream_u32(vin + pos) : (Val)0;
-      }
+      for (int u = 0; u < ITEMS; ++u)
+        v[u] = (FULL || pos0 + u * 32 < nvalid) ? (Val)ld_stream_u32(vin + u * 32) : (Val)0;
     }
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = v[u];
@@ -524,12 +537,12 @@ partition_pass_kernel(const PassArgs a) {
     }
     uint32_t base;
     if (SCATTER) {
-      uint64_t b = (uint64_t)tid << tsh;  // rows are a permutation of 0..n-1
+      uint64_t b = (uint64_t)tid << dshift;  // rows are a permutation of 0..n-1
       base = (uint32_t)(b < n ? b : n);
     } else {
       base = a.bin_base_all[((size_t)col * kMaxPasses + a.pass) * kRadix + tid];
     }
-    s_goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
+    sm.goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
   }
   __syncthreads();
 
@@ -538,19 +551,67 @@ partition_pass_kernel(const PassArgs a) {
   uint32_t* out_small = (dst == 1 ? a.valsA : a.valsB) + (size_t)col * n;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    uint32_t pos = j * BLOCK + tid;
-    if (pos < nvalid) {
-      Key k = s_keys[pos];
-      uint32_t g = s_goff[digit(k)] + pos;
+    const uint32_t pos = j * BLOCK + tid;
+    if (FULL || pos < nvalid) {
+      const uint32_t g = sm.goff[sm.dig[pos]] + pos;
       if (SCATTER) {
-        out_small[g] = (uint32_t)k;
-        out_big[g] = (uint64_t)s_vals[pos];
+        st_u32_at(out_small, g, (uint32_t)s_keys[pos]);
+        st_u64_at(out_big, g, (uint64_t)s_vals[pos]);
       } else {
-        out_big[g] = (uint64_t)k;
-        out_small[g] = (uint32_t)s_vals[pos];
+        st_u64_at(out_big, g, (uint64_t)s_keys[pos]);
+        st_u32_at(out_small, g, (uint32_t)s_vals[pos]);
       }
     }
   }
+}
+
+template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
+__global__ void __launch_bounds__(BLOCK, MINB)
+partition_pass_kernel(const PassArgs a) {
+  constexpr int TILE = BLOCK * ITEMS;
+  constexpr int NWARPS = BLOCK / 32;
+  static_assert(BLOCK >= kRadix && BLOCK % 32 == 0, "one thread per bin is assumed");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PassSmem sm;
+  sm.big = reinterpret_cast<uint64_t*>(smem_raw);
+  sm.small_ = reinterpret_cast<uint32_t*>(sm.big + TILE);
+  sm.hist = sm.small_ + TILE;
+  sm.goff = sm.hist + NWARPS * kRadix;
+  sm.bstart = sm.goff + kRadix;
+  sm.wsum = sm.bstart + kRadix;
+  uint32_t* s_tile = sm.wsum + 8;
+  sm.dig = reinterpret_cast<uint8_t*>(s_tile + 4);
+
+  const int col = blockIdx.y;
+  const int tid = threadIdx.x;
+  // SORT:    reads (keys, rows)[src] (or the raw column), writes (keys, rows)[dst]
+  // SCATTER: reads rows + staged values from buffer "other", writes rows + values to "final"
+  int src, dst;
+  uint32_t dshift;
+  KeyMap map;
+  map.kmin = map.g0 = map.g = map.neg_al = 0;
+  map.sh = 0;
+  map.exact = true;
+  if (SCATTER) {
+    dst = a.plan[col].final_buf;
+    src = (dst == 1) ? 2 : 1;
+    dshift = (uint32_t)a.shift;
+  } else {
+    if (!a.plan[col].run[a.pass]) return;
+    src = a.plan[col].src[a.pass];
+    dst = (src == 1) ? 2 : 1;
+    map = load_key_map(a.kminmax, col, a.window_bits);
+    dshift = map.sh + (uint32_t)a.pass * kRadixBits;
+  }
+  if (tid == 0) *s_tile = atomicAdd(&a.tile_counter[col], 1u);
+  for (int i = tid; i < NWARPS * kRadix; i += BLOCK) sm.hist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = *s_tile;
+  const uint32_t nvalid = min((uint32_t)TILE, a.n - tile * (uint32_t)TILE);
+  if (nvalid == (uint32_t)TILE)
+    pass_body<BLOCK, ITEMS, SCATTER, true>(a, sm, col, tile, nvalid, src, dst, dshift, map);
+  else
+    pass_body<BLOCK, ITEMS, SCATTER, false>(a, sm, col, tile, nvalid, src, dst, dshift, map);
 }
 
 // Second half of the scatter: out[row] = value for (row, value) pairs that are already grouped by
@@ -613,7 +674,7 @@ const SortCfg& sort_cfg() {
 template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
 int launch_pass(const PassArgs& a, int ncols, cudaStream_t stream) {
   auto kern = partition_pass_kernel<BLOCK, ITEMS, MINB, SCATTER>;
-  constexpr size_t smem = (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + 2 * kRadix * 4 + 8 * 4 + 16;
+  constexpr size_t smem = (size_t)BLOCK * ITEMS * 13 + (size_t)(BLOCK / 32) * kRadix * 4 + 2 * kRadix * 4 + 8 * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     PBL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -681,8 +742,8 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
     set_last_error("sort_columns_f64: n exceeds 2^30-1 rows per column");
     return kBadShape;
   }
-  if (window_bits != 40 && window_bits != 64) {
-    set_last_error("sort_columns_f64: window_bits must be 40 or 64");
+  if (window_bits != 32 && window_bits != 64) {
+    set_last_error("sort_columns_f64: window_bits must be 32 or 64");
     return kBadShape;
   }
   const int npasses = window_bits / kRadixBits;
@@ -708,8 +769,8 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
     int per_col = (int)(((size_t)n + HB * HU - 1) / (HB * HU));
     int want = (sms * 4 + ncols - 1) / ncols;  // ~4 resident blocks per SM over the batch
     dim3 grid((unsigned)std::max(1, std::min(per_col, want)), (unsigned)ncols);
-    if (npasses == 5)
-      sort_hist_kernel<HB, HU, 5><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,
+    if (npasses == 4)
+      sort_hist_kernel<HB, HU, 4><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,
                                                           buf.kminmax, window_bits);
     else
       sort_hist_kernel<HB, HU, 8><<<grid, HB, 0, stream>>>(in, row_stride, col_stride, n, buf.hist,

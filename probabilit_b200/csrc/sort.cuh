@@ -5,25 +5,26 @@
 // src/probabilit/correlation.py:394 and :422) and np.sort (:423).
 //
 // Layout in HBM (all SoA, one contiguous run per column):
-//   keys  [ncols][n]  u64   order-preserving image of the fp64 values (common.cuh::flip_f64),
-//                           -0.0 stored as +0.0 (they tie in the reference; the sign travels in
-//                           bit 31 of the payload and is restored when the sorted column is read)
+//   keys  [ncols][n]  u64   COMPACT order-preserving image of the fp64 values (common.cuh::flip_f64
+//                           followed by KeyMap's gap removal), -0.0 stored as +0.0 (they tie in
+//                           the reference; the sign travels in bit 31 of the payload and is
+//                           restored when the sorted column is read)
 //   vals  [ncols][n]  u32   source row of each key (bits 0..29), bit 31 = "was -0.0"
 //   hist  [ncols][8][256] u32   digit histograms -> exclusive bin bases
 //   status[ncols][ntiles][256] u32   look-back words: bit31 inclusive, bit30 partial, 30-bit count
-//   kminmax[ncols][2] u64   smallest / largest key of the column
+//   kminmax[ncols][4] u64   smallest / largest key of the column, largest negative / smallest positive key
 // Columns are independent: blockIdx.y is the column, so one launch per digit pass covers the
 // whole batch.  The first pass reads the caller's doubles in place (any row stride) and
 // synthesises the payload (row index), so X is never copied or converted up front.
 //
-// WINDOWED SORT.  The passes do not sort on all 64 key bits: they sort on the `window_bits`
-// (40 by default -> 5 passes instead of 8) most significant bits of (key - kmin), i.e. on a
-// monotone image of the key.  Keys that collide in the window end up adjacent but possibly out
-// of order; the consumer (post_sort_kernel in ic.cu) completes the order inside each run of
-// equal window values, which are short for any data whose distinct values are not packed more
-// densely than 2^-40 of the column's range.  If a run of distinct keys is too long to complete
-// there, a flag is raised and the caller repeats the sort with window_bits = 64 (plain, exact
-// 8-pass LSD sort).  Results are identical either way.
+// WINDOWED SORT.  The passes do not sort on all 64 key bits: they sort on a 32-bit monotone image
+// of the key (populated exponent range + top mantissa bits, see KeyMap) -> 4 digit passes instead
+// of 8.  Keys that collide in the window end up adjacent but possibly out of order; the consumer
+// (post_sort_kernel in ic.cu) completes the order inside each run of equal window values, which
+// are short unless the distinct values are packed more densely than 2^-32 of the column's range.
+// If a run of distinct keys is too long to complete there, a flag is raised and the caller
+// repeats the sort with window_bits = 64 (plain, exact 8-pass LSD sort).  Results are identical
+// either way.
 //
 // Digit passes in which every key of a column has the same digit are skipped on the device
 // (no host round trip): the scan kernel records, per column and pass, which ping-pong buffer
@@ -50,7 +51,8 @@ enum SortFlag : int {
   kFlagNaN = 1,         // NaN in the input column
   kFlagNotPD = 2,       // (Iman-Conover) rank correlation not positive definite
   kFlagReserved = 3,
-  kFlagWindowRetry = 4  // a run of distinct keys inside one window value was too long
+  kFlagWindowRetry = 4, // a run of distinct keys inside one window value was too long
+  kFlagNegZeroCol0 = 5  // column 0 of X holds a -0.0 (its tie-runs then mix the two zeros)
 };
 
 // Per (column, pass) routing decided on the device by sort_scan_kernel.
@@ -61,33 +63,78 @@ struct PassPlan {
   uint8_t pad[7];
 };
 
-// Monotone map key -> window value:  (key - kmin) >> sh, with kmin a multiple of 2^sh, fits in
-// window_bits bits.  Because kmin is aligned, two keys share a window value iff
-// ((a ^ b) >> sh) == 0.
+// Monotone map key -> window value.
+//   window_bits == 32 (default): SEGMENTED window.  In key space an fp64 column that straddles zero
+//   (or contains zeros) is mostly empty: all the binades between the smallest |x| present and the
+//   denormals lie between its negative and positive keys.  The map removes those gaps,
+//       a(key) = key - kmin                          key <  Z   (negative values)
+//                neg_al                              key == Z   (+-0.0, Z = key of +0.0)
+//                neg_al + 2^sh + (key - kpos_min)    key >  Z   (positive values)
+//   with kpos_min the smallest key > Z and neg_al = kneg_max - kmin + 1 rounded up to 2^sh, and
+//   keeps the 32 most significant bits of a's range:  w = a >> sh.  a is strictly increasing in the
+//   key, so w is a monotone image; what remains are (populated exponent range, top mantissa bits):
+//   a column spanning 2^e binades keeps 32 - e mantissa bits, e.g. 26 bits (6.7e7 window values per
+//   binade) for 1e8 normal samples -> 4 digit passes instead of 8, robust to heavy tails.
+//   window_bits == 64: the key itself (exact 8-pass LSD sort, the fall-back).
+// kminmax holds 4 words per column: kmin, kmax, kneg_max (largest key < Z, 0 if none),
+// kpos_min (smallest key > Z, ~0 if none).
+constexpr uint64_t kZeroKey = 0x8000000000000000ull;
+constexpr int kMinMaxWords = 4;
 struct KeyMap {
-  uint64_t kmin;
+  uint64_t kmin;    // subtracted from negative keys
+  uint64_t g0;      // subtracted from the zero key
+  uint64_t g;       // subtracted from positive keys
+  uint64_t neg_al;  // a(zero key); negatives are below it, positives at or above neg_al + 2^sh
   uint32_t sh;
+  bool exact;
 };
 __device__ __forceinline__ KeyMap load_key_map(const uint64_t* __restrict__ kminmax, int col,
                                                int window_bits) {
   KeyMap m;
   m.kmin = 0;
+  m.g0 = 0;
+  m.g = 0;
+  m.neg_al = 0;
   m.sh = 0;
-  if (window_bits < 64) {
-    const uint64_t lo = kminmax[2 * col], hi = kminmax[2 * col + 1];
-    const uint64_t range = hi >= lo ? hi - lo : 0;
-    const int bits = 64 - __clzll((long long)range);
-    uint32_t sh = bits > window_bits ? (uint32_t)(bits - window_bits) : 0u;
-    // aligning kmin down can widen the span by one window value: make sure it still fits
-    if ((((hi >> sh) - (lo >> sh)) >> window_bits) != 0) ++sh;
+  m.exact = window_bits >= 64;
+  if (!m.exact) {
+    const uint64_t* q = kminmax + (size_t)kMinMaxWords * col;
+    const uint64_t kmin = q[0], kmax = q[1], kneg_max = q[2], kpos_min = q[3];
+    const uint64_t span_neg = kmin < kZeroKey ? kneg_max - kmin + 1 : 0;
+    const uint64_t span_pos = kmax > kZeroKey ? kmax - kpos_min + 1 : 0;
+    // zero gets a window value of its own and the positives start on a fresh one (the segments are
+    // aligned to 2^sh), so that heavily tied neighbours of zero (0 / 1 counts) never share a window
+    const uint64_t rough = span_neg + 1 + span_pos;  // < 2^64: both spans are < 2^63
+    const int bits = 64 - __clzll((long long)rough);
+    uint32_t sh = bits > 32 ? (uint32_t)(bits - 32) : 0u;
+    uint64_t neg_al = 0, unit = 1;
+    for (int it = 0; it < 3; ++it) {
+      unit = 1ull << sh;
+      neg_al = (span_neg + unit - 1) & ~(unit - 1);
+      const uint64_t last = neg_al + unit + span_pos - (span_pos ? 1 : 0);  // largest a
+      if ((last >> sh) >> 32) ++sh; else break;
+    }
+    m.kmin = kmin;
+    m.g0 = kZeroKey - neg_al;
+    m.g = kpos_min - (neg_al + unit);
+    m.neg_al = neg_al;
     m.sh = sh;
-    m.kmin = (lo >> sh) << sh;
   }
   return m;
 }
-__device__ __forceinline__ uint64_t window_value(uint64_t key, const KeyMap& m) {
-  return (key - m.kmin) >> m.sh;
+// The sort buffers hold COMPACT keys a(key): the order is the key order, the digit of pass p is
+// (a >> (sh + 8 p)) & 255 -- one shift and a mask -- and a is inverted when the sorted column is read.
+__device__ __forceinline__ uint64_t compact_key(uint64_t key, const KeyMap& m) {
+  if (m.exact) return key;
+  const uint64_t base = key > kZeroKey ? m.g : (key == kZeroKey ? m.g0 : m.kmin);
+  return key - base;
 }
+__device__ __forceinline__ uint64_t expand_key(uint64_t a, const KeyMap& m) {
+  if (m.exact) return a;
+  return a > m.neg_al ? a + m.g : (a == m.neg_al ? kZeroKey : a + m.kmin);
+}
+// window value / window equality of COMPACT keys
+__device__ __forceinline__ uint64_t window_value(uint64_t a, const KeyMap& m) { return a >> m.sh; }
 __device__ __forceinline__ bool same_window(uint64_t a, uint64_t b, const KeyMap& m) {
   return ((a ^ b) >> m.sh) == 0;
 }
@@ -101,7 +148,7 @@ struct SortBuffers {
   uint32_t* status = nullptr;        // [ncols][ntiles][256]
   uint32_t* tile_counter = nullptr;  // [8 passes + 1 scatter pass][ncols]
   PassPlan* plan = nullptr;          // [ncols]
-  uint64_t* kminmax = nullptr;       // [ncols][2]
+  uint64_t* kminmax = nullptr;       // [ncols][4], see KeyMap
   uint32_t* error_flag = nullptr;    // [8], see SortFlag
 };
 

@@ -97,7 +97,8 @@ def test_heavy_ties_partitioned_scatter():
 
 
 def test_dense_cluster_falls_back_to_full_sort():
-    """Distinct values packed more densely than 2^-40 of the column's range: the 40-bit sort window
+    """Distinct values packed more densely than the 32-bit sort window resolves (here 2^-52 apart in a
+    column spanning ~2000 binades): the window
     cannot separate them, the post-sort kernel raises the retry flag and the plan repeats the
     transform with the exact 64-bit sort.  Output must still be bit-exact."""
     from probabilit_b200 import ImanConover
@@ -116,7 +117,7 @@ def test_dense_cluster_falls_back_to_full_sort():
 
 
 def test_window_collisions_are_completed_in_tile():
-    """Many short runs of distinct keys sharing a 40-bit window value (no fallback needed)."""
+    """Many short runs of distinct keys sharing a window value (no fallback needed)."""
     rng = np.random.default_rng(13)
     n, k = 150_000, 2
     X = np.asfortranarray(rng.normal(size=(n, k)))
