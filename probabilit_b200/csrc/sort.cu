@@ -253,7 +253,7 @@ __global__ void tile_scan_kernel(uint32_t* __restrict__ tile_counts,
 // so that (warp, item, lane) order == position order (every LSD pass must be stable).
 //   load -> early per-warp digit counts -> tile counts published for the tiles behind us
 //   -> ballot-based ranking, one shared-memory atomic per distinct digit and warp
-//   -> scatter key + payload + digit byte into shared memory in digit order -> look back for the
+//   -> scatter key + payload into shared memory in digit order -> look back for the
 //   exclusive tile prefix per bin -> coalesced runs out to HBM.
 // SCATTER = false: radix digit pass of the sort  (key u64 = compact key, payload u32 = row).
 // SCATTER = true : first half of the "scatter by row" step that follows each sort: key u32 =
@@ -267,7 +267,6 @@ __global__ void tile_scan_kernel(uint32_t* __restrict__ tile_counts,
 // B200 has about half the integer issue rate per byte of HBM bandwidth of an H100), so the code
 // is organised to minimise ALU instructions per key:
 //   * keys are stored COMPACT (sort.cuh): the digit is one 64-bit shift + mask;
-//   * the digit is computed once and travels through shared memory as a byte;
 //   * full tiles (all but the last tile of a column) run a path without any bounds predicate;
 //   * global addresses are formed with mad.wide (fma pipe) instead of shift/add pairs.
 // --------------------------------------------------------------------------------------
@@ -309,7 +308,6 @@ __device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t
 struct PassSmem {
   uint64_t* big;      // [TILE] 8-byte member
   uint32_t* small_;   // [TILE] 4-byte member
-  uint8_t* dig;       // [TILE] digit of the element at each tile-local (digit-ordered) position
   uint32_t* hist;     // [NWARPS][kRadix]
   uint32_t* goff;     // [kRadix] global slot - tile position
   uint32_t* bstart;   // [kRadix] tile-local bin start
@@ -429,7 +427,16 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
   //      shared-memory atomic per digit group, issued by its highest lane, (3) broadcast + lane
   //      offset. ----
   uint32_t rank[ITEMS];
-  {
+  if (SCATTER) {
+    // scatter-by-row needs no stable order inside a bin (rows are unique and the second half places
+    // every element by its row): one returning shared atomic per key instead of the 8-ballot match
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u) {
+      uint32_t r;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(wh_addr + dig[u] * 4u), "r"(1u) : "memory");
+      rank[u] = r;
+    }
+  } else {
     const uint32_t lt = lanemask_lt();
     uint32_t m[ITEMS];
 #pragma unroll
@@ -468,7 +475,6 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
   for (int u = 0; u < ITEMS; ++u) {
     rank[u] += sm.bstart[dig[u]];
     s_keys[rank[u]] = key[u];
-    sm.dig[rank[u]] = (uint8_t)dig[u];
   }
   if (!SCATTER && src == 0) {
 #pragma unroll
@@ -496,39 +502,34 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
     uint32_t excl = 0;
     if (a.use_lookback) {
       if (tile != 0) {
-        // the 4 nearest predecessors are fetched together (one L2 round trip instead of up to 4)
-        constexpr int LB = 4;
-        uint32_t pre[LB];
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-          int64_t t = (int64_t)tile - 1 - i;
-          pre[i] = (t >= 0) ? ld_relaxed_u32(&st[(size_t)t * kRadix + tid]) : kFlagInclusive;
-        }
+        // walk back over the predecessors LB at a time: the LB status words are fetched together
+        // (one L2 round trip per batch instead of one per predecessor), consumed in order, and the
+        // walk stops at the first inclusive word; an unpublished word restarts the batch there
+        constexpr int LB = 8;
         int64_t t = (int64_t)tile - 1;
         bool done = false;
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-          if (!done) {
-            uint32_t w = pre[i];
-            if ((w & (kFlagInclusive | kFlagPartial)) == 0) break;  // not published yet: poll below
-            excl += w & kValueMask;
-            if (w & kFlagInclusive) done = true;
-            --t;
-          }
-        }
         uint32_t spins = 0;
         while (!done) {
-          uint32_t w = ld_relaxed_u32(&st[(size_t)t * kRadix + tid]);
-          if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
-            if (++spins > kSpinLimit) {
-              atomicExch(&a.error_flag[kFlagWatchdog], 1u);
-              break;
+          uint32_t pre[LB];
+#pragma unroll
+          for (int i = 0; i < LB; ++i)
+            pre[i] = (t - i >= 0) ? ld_relaxed_u32(&st[(size_t)(t - i) * kRadix + tid]) : kFlagInclusive;
+#pragma unroll
+          for (int i = 0; i < LB; ++i) {
+            if (!done) {
+              const uint32_t w = pre[i];
+              if ((w & (kFlagInclusive | kFlagPartial)) == 0) {  // not published yet: poll again from here
+                if (++spins > kSpinLimit) {
+                  atomicExch(&a.error_flag[kFlagWatchdog], 1u);
+                  done = true;
+                }
+                break;
+              }
+              excl += w & kValueMask;
+              --t;
+              if (w & kFlagInclusive) done = true;
             }
-            continue;
           }
-          excl += w & kValueMask;
-          if (w & kFlagInclusive) break;
-          --t;
         }
         st_relaxed_u32(&st[(size_t)tile * kRadix + tid], ((excl + cnt) & kValueMask) | kFlagInclusive);
       }
@@ -553,12 +554,14 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t pos = j * BLOCK + tid;
     if (FULL || pos < nvalid) {
-      const uint32_t g = sm.goff[sm.dig[pos]] + pos;
+      const Key k = s_keys[pos];
+      const uint32_t d = SCATTER ? ((uint32_t)k >> dshift) : ((uint32_t)((uint64_t)k >> dshift) & (uint32_t)(kRadix - 1));
+      const uint32_t g = sm.goff[d] + pos;
       if (SCATTER) {
-        st_u32_at(out_small, g, (uint32_t)s_keys[pos]);
+        st_u32_at(out_small, g, (uint32_t)k);
         st_u64_at(out_big, g, (uint64_t)s_vals[pos]);
       } else {
-        st_u64_at(out_big, g, (uint64_t)s_keys[pos]);
+        st_u64_at(out_big, g, (uint64_t)k);
         st_u32_at(out_small, g, (uint32_t)s_vals[pos]);
       }
     }
@@ -580,7 +583,6 @@ partition_pass_kernel(const PassArgs a) {
   sm.bstart = sm.goff + kRadix;
   sm.wsum = sm.bstart + kRadix;
   uint32_t* s_tile = sm.wsum + 8;
-  sm.dig = reinterpret_cast<uint8_t*>(s_tile + 4);
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
@@ -665,6 +667,9 @@ const SortCfg& sort_cfg() {
       case 3: g_cfg = {384, 12}; break;
       case 5: g_cfg = {256, 8}; break;
       case 0: g_cfg = {256, 16}; g_cfg.minb = 2; break;
+      case 7: g_cfg = {256, 12}; g_cfg.minb = 4; break;
+      case 8: g_cfg = {512, 8}; g_cfg.minb = 3; break;
+      case 9: g_cfg = {384, 8}; g_cfg.minb = 4; break;
       default: g_cfg = {256, 16}; g_cfg.minb = 3; break;
     }
   }
@@ -674,7 +679,7 @@ const SortCfg& sort_cfg() {
 template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
 int launch_pass(const PassArgs& a, int ncols, cudaStream_t stream) {
   auto kern = partition_pass_kernel<BLOCK, ITEMS, MINB, SCATTER>;
-  constexpr size_t smem = (size_t)BLOCK * ITEMS * 13 + (size_t)(BLOCK / 32) * kRadix * 4 + 2 * kRadix * 4 + 8 * 4 + 16;
+  constexpr size_t smem = (size_t)BLOCK * ITEMS * 12 + (size_t)(BLOCK / 32) * kRadix * 4 + 2 * kRadix * 4 + 8 * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     PBL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -687,7 +692,10 @@ int launch_pass(const PassArgs& a, int ncols, cudaStream_t stream) {
 template <bool SCATTER>
 int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
   const SortCfg& c = sort_cfg();
+  if (c.block == 512 && c.items == 8 && c.minb == 3) return launch_pass<512, 8, 3, SCATTER>(a, ncols, stream);
   if (c.block == 512 && c.items == 8) return launch_pass<512, 8, 2, SCATTER>(a, ncols, stream);
+  if (c.block == 256 && c.items == 12 && c.minb == 4) return launch_pass<256, 12, 4, SCATTER>(a, ncols, stream);
+  if (c.block == 384 && c.items == 8) return launch_pass<384, 8, 4, SCATTER>(a, ncols, stream);
   if (c.block == 256 && c.items == 12) return launch_pass<256, 12, 3, SCATTER>(a, ncols, stream);
   if (c.block == 384 && c.items == 12) return launch_pass<384, 12, 2, SCATTER>(a, ncols, stream);
   if (c.block == 256 && c.items == 8) return launch_pass<256, 8, 5, SCATTER>(a, ncols, stream);
