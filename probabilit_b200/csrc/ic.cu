@@ -33,7 +33,8 @@ constexpr int kPostItems = 4;
 constexpr int kPostTile = kPostBlock * kPostItems;
 constexpr int kHalo = 64;                      // window values may repeat in runs of < kHalo keys
 constexpr int kWin = kPostTile + 2 * kHalo;
-constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 128;
+constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 128 +
+                             3 * kRadix * 4 + 16;
 
 __device__ __forceinline__ uint32_t block_excl_prefix_max(uint32_t v, uint32_t* s_w) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,7 +95,9 @@ __global__ void __launch_bounds__(kPostBlock)
 post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB,
                  const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
                  int window_bits, uint32_t n, double* __restrict__ sortedX,
-                 const double* __restrict__ vdw, uint32_t* __restrict__ flags, int col_base) {
+                 const double* __restrict__ vdw, uint32_t* __restrict__ flags, int col_base,
+                 int part_shift, uint32_t* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                 int ntiles) {
   extern __shared__ __align__(16) unsigned char psm[];
   uint64_t* s_raw = reinterpret_cast<uint64_t*>(psm);        // [kWin] keys as the sort left them
   uint64_t* s_key = s_raw + kWin;                            // [kWin] completed order
@@ -104,9 +107,26 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* s_end = s_start + kPostTile;                     // [kPostTile]
   uint32_t* s_w = s_end + kPostTile;                         // [kPostBlock / 32]
   uint32_t* s_lohi = s_w + kPostBlock / 32;                  // [2]
+  uint32_t* s_cnt = s_lohi + 4;                              // [kRadix] elements per destination window
+  uint32_t* s_bstart = s_cnt + kRadix;                       // [kRadix]
+  uint32_t* s_goff = s_bstart + kRadix;                      // [kRadix]
+  uint32_t* s_ticket = s_goff + kRadix;                      // [1]
+  // staging of the partitioned (value, row) pairs: the raw window copies are dead by then
+  double* s_pval = reinterpret_cast<double*>(s_raw);         // [kPostTile]
+  uint32_t* s_prow = s_rawv;                                 // [kPostTile]
 
   const int col = blockIdx.y;
   const int tid = threadIdx.x;
+  const bool partition = part_shift < 32;
+  // tiles take tickets so that the look-back between tiles can never wait on a tile that has not
+  // started (blockIdx order is not a scheduling guarantee)
+  uint32_t tile = blockIdx.x;
+  if (partition) {
+    if (tid == 0) *s_ticket = atomicAdd(&tile_counter[col], 1u);
+    if (tid < kRadix) s_cnt[tid] = 0;
+    __syncthreads();
+    tile = *s_ticket;
+  }
   const int fb = plan[col].final_buf;
   const uint64_t* keys = (fb == 1 ? keysA : keysB) + (size_t)col * n;
   const uint32_t* rows_in = (fb == 1 ? valsA : valsB) + (size_t)col * n;
@@ -114,7 +134,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* rows_out = (fb == 1 ? valsB : valsA) + (size_t)col * n;
   double* sx = sortedX + (size_t)col * n;
   const KeyMap map = load_key_map(kminmax, col, window_bits);
-  const uint32_t tile_start = blockIdx.x * (uint32_t)kPostTile;
+  const uint32_t tile_start = tile * (uint32_t)kPostTile;
   const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
   const int64_t wbase = (int64_t)tile_start - kHalo;  // global index of window slot 0
 
@@ -252,9 +272,14 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
     __syncthreads();
   }
 
+  // ---- (3) the value every source row must receive ----
+  double out_val[kPostItems];
+  uint32_t out_row[kPostItems];
 #pragma unroll
   for (int j = 0; j < kPostItems; ++j) {
     uint32_t p = j * kPostBlock + tid;
+    out_val[j] = 0.0;
+    out_row[j] = 0;
     if (p < nvalid) {
       uint32_t g = tile_start + p;
       uint32_t s = g, e = g;
@@ -263,11 +288,11 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
         e = s_end[p];
       }
       const uint32_t row = s_row[kHalo + p];
-      rows_out[g] = row & kRowMask;
+      out_row[j] = row & kRowMask;
       if (MODE == 2) {
         // scipy.stats.rankdata(x) itself (average ranks as doubles): the Spearman mode of
         // CorrelationMatrix, correlation.py:835-837
-        stage[g] = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
+        out_val[j] = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
       } else if (MODE == 0) {
         double sc;
         if (s == e) {
@@ -276,13 +301,114 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
           double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
           sc = ndtri(__ddiv_rn(avg, (double)((uint64_t)n + 1ull)));
         }
-        stage[g] = sc;
+        out_val[j] = sc;
         sx[g] = (row & kNegZeroFlag) ? -0.0 : key_to_double(expand_key(s_key[kHalo + p], map));
         if ((row & kNegZeroFlag) && col + col_base == 0) flags[kFlagNegZeroCol0] = 1u;
       } else {
         uint32_t m = s + (e - s) / 2;
-        stage[g] = sx[m];
+        out_val[j] = sx[m];
       }
+    }
+  }
+  if (!partition) {  // short columns: scatter_rows_kernel delivers straight from sorted order
+#pragma unroll
+    for (int j = 0; j < kPostItems; ++j) {
+      uint32_t p = j * kPostBlock + tid;
+      if (p < nvalid) {
+        rows_out[tile_start + p] = out_row[j];
+        stage[tile_start + p] = out_val[j];
+      }
+    }
+    return;
+  }
+
+  // ---- (4) first half of the scatter by row, fused: group the tile's (row, value) pairs by
+  //      destination window (row >> part_shift, <= 256 windows of L2 size) with a chained scan
+  //      between tiles, like partition_pass_kernel<SCATTER> but without its extra round trip of
+  //      the pairs through HBM.  No stable order is needed inside a window. ----
+  uint32_t slot[kPostItems];
+#pragma unroll
+  for (int j = 0; j < kPostItems; ++j) {
+    uint32_t p = j * kPostBlock + tid;
+    slot[j] = 0;
+    if (p < nvalid) slot[j] = atomicAdd(&s_cnt[out_row[j] >> part_shift], 1u);
+  }
+  __syncthreads();
+  uint32_t cnt = 0, bin_start = 0;
+  uint32_t* st = status + (size_t)col * ntiles * kRadix;
+  if (tid < kRadix) {
+    cnt = s_cnt[tid];
+    st_relaxed_u32(&st[(size_t)tile * kRadix + tid], cnt | (tile == 0 ? kFlagInclusive : kFlagPartial));
+  }
+  {
+    // exclusive scan of the 256 counts (threads >= 256 carry zeros)
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    bin_start = incl - cnt;
+    for (uint32_t w = 0; w < warp; ++w) bin_start += s_w[w];
+    if (tid < kRadix) s_bstart[tid] = bin_start;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPostItems; ++j) {
+    uint32_t p = j * kPostBlock + tid;
+    if (p < nvalid) {
+      const uint32_t q = s_bstart[out_row[j] >> part_shift] + slot[j];
+      s_pval[q] = out_val[j];
+      s_prow[q] = out_row[j];
+    }
+  }
+  if (tid < kRadix) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      constexpr int LB = 8;
+      int64_t t = (int64_t)tile - 1;
+      bool done = false;
+      uint32_t spins = 0;
+      while (!done) {
+        uint32_t pre[LB];
+#pragma unroll
+        for (int i = 0; i < LB; ++i)
+          pre[i] = (t - i >= 0) ? ld_relaxed_u32(&st[(size_t)(t - i) * kRadix + tid]) : kFlagInclusive;
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+          if (!done) {
+            const uint32_t w = pre[i];
+            if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
+              if (++spins > (1u << 24)) {
+                atomicExch(&flags[kFlagWatchdog], 1u);
+                done = true;
+              }
+              break;
+            }
+            excl += w & kValueMask;
+            --t;
+            if (w & kFlagInclusive) done = true;
+          }
+        }
+      }
+      st_relaxed_u32(&st[(size_t)tile * kRadix + tid], ((excl + cnt) & kValueMask) | kFlagInclusive);
+    }
+    const uint64_t b = (uint64_t)tid << part_shift;  // rows are a permutation of 0..n-1
+    const uint32_t base = (uint32_t)(b < n ? b : n);
+    s_goff[tid] = base + excl - bin_start;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPostItems; ++j) {
+    uint32_t p = j * kPostBlock + tid;
+    if (p < nvalid) {
+      const uint32_t r = s_prow[p];
+      const uint32_t g = s_goff[r >> part_shift] + p;
+      rows_out[g] = r;
+      stage[g] = s_pval[p];
     }
   }
 }
@@ -807,17 +933,22 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
                                    p->window_bits, sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
     PBL_RETURN_IF(post_sort_attr());
+    int shift = 32, ntiles = 0;
+    uint32_t* counter = nullptr;
+    PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), 1, p->use_lookback, kPostTile, &shift, &ntiles, &counter,
+                                  stream));
     if (ranks_only)
       post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
+          ntiles);
     else
       post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
+          ntiles);
     PBL_LAUNCH_CHECK();
-    PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n,
-                                 p->use_lookback, stream));
+    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n, stream));
   }
   return kOk;
 }
@@ -892,12 +1023,17 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
                                    sort_view(p), p->use_lookback, stream));
     dim3 grid((unsigned)((n + kPostTile - 1) / kPostTile), (unsigned)nb);
     PBL_RETURN_IF(post_sort_attr());
+    int shift = 32, ntiles = 0;
+    uint32_t* counter = nullptr;
+    PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), row_stride, p->use_lookback, kPostTile, &shift, &ntiles,
+                                  &counter, stream));
     post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
         p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c);
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
+        ntiles);
     PBL_LAUNCH_CHECK();
-    PBL_RETURN_IF(scatter_by_row(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride,
-                                 col_stride, p->use_lookback, stream));
+    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride, col_stride,
+                               stream));
   }
   return kOk;
 }

@@ -737,7 +737,8 @@ void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys) {
 int sort_tile_size() { return sort_cfg().block * sort_cfg().items; }
 
 size_t sort_status_bytes(int ncols, uint32_t n) {
-  size_t tile = (size_t)sort_tile_size();
+  // the fused post-sort partition (ic.cu) works on 2048-element tiles: size for the smaller tile
+  size_t tile = std::min<size_t>((size_t)sort_tile_size(), 2048);
   size_t ntiles = ((size_t)n + tile - 1) / tile;
   return (size_t)ncols * ntiles * kRadix * sizeof(uint32_t);
 }
@@ -844,35 +845,31 @@ static int scatter_shift_for(uint32_t n) {
   return bits > 19 ? std::max(19, bits - 8) : 32;
 }
 
-int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
-                   int64_t col_stride, bool use_lookback, cudaStream_t stream) {
-  if (n == 0 || ncols <= 0) return kOk;
-  const int shift = scatter_shift_for(n);
-  const bool partitioned = shift < 32 && use_lookback && row_stride == 1;
-  if (partitioned) {
-    const int tile = sort_tile_size();
-    const int ntiles = (int)(((size_t)n + tile - 1) / tile);
-    PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, sort_status_bytes(ncols, n), stream));
-    PassArgs a{};
-    a.keysA = buf.keysA;
-    a.keysB = buf.keysB;
-    a.valsA = buf.valsA;
-    a.valsB = buf.valsB;
-    a.status = buf.status;
-    a.tile_counter = buf.tile_counter + (size_t)kMaxPasses * ncols;
-    a.plan = buf.plan;
-    a.error_flag = buf.error_flag;
-    a.n = n;
-    a.shift = shift;
-    a.ntiles = ntiles;
-    a.use_lookback = 1;
-    PBL_CUDA_CHECK(cudaMemsetAsync(a.tile_counter, 0, (size_t)ncols * 4, stream));
-    PBL_RETURN_IF(launch_pass_cfg<true>(a, ncols, stream));
-    PBL_LAUNCH_CHECK();
+// Scatter by row, second half.  The consumer of the sort (post_sort_kernel in ic.cu) leaves
+// (row, value) pairs in the "other" ping-pong buffer, already grouped by destination window when
+// scatter_prepare() returned a shift < 32; this kernel delivers value -> out[row].
+int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_stride, bool use_lookback,
+                    int consumer_tile, int* shift_out, int* ntiles_out, uint32_t** tile_counter_out,
+                    cudaStream_t stream) {
+  int shift = scatter_shift_for(n);
+  if (!(use_lookback && row_stride == 1)) shift = 32;
+  const int ntiles = (int)(((size_t)n + consumer_tile - 1) / consumer_tile);
+  *shift_out = shift;
+  *ntiles_out = ntiles;
+  *tile_counter_out = buf.tile_counter + (size_t)kMaxPasses * ncols;
+  if (shift < 32) {
+    PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, (size_t)ncols * ntiles * kRadix * sizeof(uint32_t), stream));
+    PBL_CUDA_CHECK(cudaMemsetAsync(*tile_counter_out, 0, (size_t)ncols * 4, stream));
   }
+  return kOk;
+}
+
+int scatter_rows(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
+                 int64_t col_stride, cudaStream_t stream) {
+  if (n == 0 || ncols <= 0) return kOk;
   dim3 grid((unsigned)(((size_t)n + 2047) / 2048), (unsigned)ncols);
   scatter_rows_kernel<<<grid, 256, 0, stream>>>(buf.keysA, buf.keysB, buf.valsA, buf.valsB, buf.plan,
-                                               n, partitioned ? 1 : 0, out, row_stride, col_stride);
+                                               n, 0, out, row_stride, col_stride);
   PBL_LAUNCH_CHECK();
   return kOk;
 }

@@ -171,11 +171,16 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
                      int ncols, int window_bits, const SortBuffers& buf, bool use_lookback,
                      cudaStream_t stream);
 
-// "Scatter by row" that follows each sort: out[col][rows[p] * row_stride] = value[p], where the
-// caller staged rows[] in vals[other] and value[] in keys[other] ("other" = the buffer that is
-// not plan[c].final_buf).  For long columns it runs as a partition pass into <= 256 L2-sized row
-// windows followed by a window-local scatter (see sort.cu); short columns are scattered directly.
-int scatter_by_row(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
-                   int64_t col_stride, bool use_lookback, cudaStream_t stream);
+// "Scatter by row" that follows each sort: out[col][row * row_stride] = value for the (row, value)
+// pairs the sort's consumer staged in the "other" ping-pong buffer (vals[other] / keys[other]).
+// For long columns the consumer first groups the pairs into <= 256 L2-sized row windows (a fused
+// partition step, chained scan between its tiles of `consumer_tile` elements): scatter_prepare
+// returns the window shift (32 = no grouping), the tile count and the ticket counter, and clears
+// the look-back words.  scatter_rows then writes every 128 B line of the output once, from L2.
+int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_stride, bool use_lookback,
+                    int consumer_tile, int* shift_out, int* ntiles_out, uint32_t** tile_counter_out,
+                    cudaStream_t stream);
+int scatter_rows(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
+                 int64_t col_stride, cudaStream_t stream);
 
 }  // namespace pbl
