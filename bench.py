@@ -29,7 +29,9 @@ if ROOT not in sys.path:
 METRIC = "iman_conover_samples_vars_per_s"
 UNIT = "samples*vars/s"
 IC_BYTES_PER_SAMPLE_VAR = 456.0  # fixed algorithmic accounting
-PASS_BYTES_PER_KEY = (7 * 24.0 + 20.0) / 8.0  # 12 B in + 12 B out per key and digit pass; pass 0 reads 8 B
+# one digit pass moves 12 B in + 12 B out per key (u64 key + u32 row); the first of the 4 passes of the
+# 32-bit window reads the 8 B double instead of 12 B
+PASS_BYTES_PER_KEY = (3 * 24.0 + 20.0) / 4.0
 
 
 def hbm_peak():
@@ -159,6 +161,30 @@ def time_cpu_port(n_rows, d, reps=1):
         oic.iman_conover(X, Ct)
         best = min(best, time.perf_counter() - t0)
     return n_rows * d / best, best
+
+
+def time_graph(n, lib):
+    """Secondary line (BASELINE.json configs[1]): the README mutual-fund graph (20 norm ppf + 40
+    arithmetic nodes) evaluated by the fused graph kernel, quantiles generated in-kernel (Philox),
+    only the sink retained.  Host wall time of the synchronous evaluation, best of 3."""
+    import probabilit_b200.modeling as m
+
+    returns = 0
+    for _ in range(20):
+        returns = returns * m.Distribution("norm", loc=1.11, scale=0.15) + 1200
+    best = float("inf")
+    for rep in range(4):
+        run = m._GraphRun(returns, m._PhiloxSource(rep, n, 20), "imanconover", [])
+        lib.pbl_stream_synchronize(None)
+        t0 = time.perf_counter()
+        run.execute()
+        lib.pbl_stream_synchronize(None)
+        if rep:
+            best = min(best, time.perf_counter() - t0)
+    return {"workload": f"README mutual-fund graph, n={n}, 20 norm ppf + 40 arithmetic nodes, in-kernel Philox, "
+                        "sink retained", "ms": best * 1e3, "samples_per_s": n / best,
+            "distribution_samples_per_s": 20 * n / best, "bound": "fp64/integer ALU (20 ndtri per 8 B written)",
+            "hbm_bytes_per_sample": 8}
 
 
 # ------------------------------------------------------------------------------------------
@@ -295,6 +321,10 @@ def run_ours(args, rank, world, local_rank):
         lib.pbl_host_free_pinned(hx)
         lib.pbl_host_free_pinned(hy)
 
+    graph = None
+    if world == 1 and args.graph_rows > 0:
+        graph = time_graph(args.graph_rows, lib)
+
     if rank != 0:
         return
     peak, peak_src = hbm_peak()
@@ -327,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
                    "rows_per_gpu": n, "d": d, "l2": "inputs (12.8 GB) far exceed the 126 MB L2",
                    "col_batch": args.col_batch},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks,
+        "clocks": clocks, "graph": graph,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -346,6 +376,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=lambda s: int(float(s)), default=3_000_000)
     ap.add_argument("--ref-rows", type=lambda s: int(float(s)), default=1_000_000)
+    ap.add_argument("--graph-rows", type=lambda s: int(float(s)), default=100_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -138,6 +138,17 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
   const int64_t wbase = (int64_t)tile_start - kHalo;  // global index of window slot 0
 
+  // the position-indexed operand of step (3) is fetched now, together with the window, so that its
+  // HBM latency is not a separate link of the tile's dependency chain: the van der Waerden score of
+  // the position (MODE 0) / the sorted marginal at the position (MODE 1; used unless the position
+  // sits in a tie-run, whose midpoint is then fetched instead)
+  double pre_val[kPostItems];
+#pragma unroll
+  for (int j = 0; j < kPostItems; ++j) {
+    const uint32_t p = j * kPostBlock + tid;
+    pre_val[j] = 0.0;
+    if (MODE != 2 && p < nvalid) pre_val[j] = ld_stream_f64((MODE == 0 ? vdw : sx) + tile_start + p);
+  }
   for (int i = tid; i < kWin; i += kPostBlock) {
     int64_t g = wbase + i;
     uint64_t k = 0;
@@ -296,7 +307,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
       } else if (MODE == 0) {
         double sc;
         if (s == e) {
-          sc = ld_stream_f64(vdw + g);  // untied: the score depends on the position only
+          sc = pre_val[j];  // untied: the score depends on the position only
         } else {
           double avg = (double)((uint64_t)s + (uint64_t)e + 2ull) * 0.5;
           sc = ndtri(__ddiv_rn(avg, (double)((uint64_t)n + 1ull)));
@@ -306,7 +317,7 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
         if ((row & kNegZeroFlag) && col + col_base == 0) flags[kFlagNegZeroCol0] = 1u;
       } else {
         uint32_t m = s + (e - s) / 2;
-        out_val[j] = sx[m];
+        out_val[j] = (m == g) ? pre_val[j] : sx[m];
       }
     }
   }
