@@ -204,6 +204,13 @@ typedef enum pbl_graph_op {
   /* ppf */
   PBL_PPF_NORM = 16, PBL_PPF_UNIFORM = 17, PBL_PPF_EXPON = 18, PBL_PPF_TRIANG = 19, PBL_PPF_GAMMA = 20,
   PBL_PPF_LOGNORM = 21, PBL_PPF_POISSON = 22, PBL_PPF_BINOM = 23, PBL_PPF_BERNOULLI = 24,
+  /* table-lookup distributions (modeling.py:825-927): operand 0 = q, src[1] = INDEX INTO inputs[] of a
+   * device table (not a slot), imm[1] = table length m, imm[2] = method
+   *   TABLE_INTERP   np.interp(q, xp, fp), table = xp[m] then fp[m]         (CumulativeDistribution)
+   *   TABLE_SEARCH   np.searchsorted(cum, q, side="right") as a double       (DiscreteDistribution)
+   *   TABLE_QUANTILE np.quantile(sorted data, q, method), table = data[m]    (EmpiricalDistribution)
+   *                  method 0 linear 1 lower 2 higher 3 nearest 4 midpoint 5 closest_observation */
+  PBL_PPF_TABLE_INTERP = 25, PBL_PPF_TABLE_SEARCH = 26, PBL_PPF_TABLE_QUANTILE = 27,
   /* binary (dst <- op(a, b)) */
   PBL_OP_ADD = 32, PBL_OP_MUL = 33, PBL_OP_SUB = 34, PBL_OP_DIV = 35, PBL_OP_POW = 36, PBL_OP_FLOORDIV = 37,
   PBL_OP_MOD = 38, PBL_OP_MAX = 39, PBL_OP_MIN = 40, PBL_OP_ATAN2 = 41, PBL_OP_LT = 42, PBL_OP_LE = 43,
@@ -213,7 +220,10 @@ typedef enum pbl_graph_op {
   PBL_OP_NEG = 64, PBL_OP_ABS = 65, PBL_OP_LOG = 66, PBL_OP_EXP = 67, PBL_OP_FLOOR = 68, PBL_OP_CEIL = 69,
   PBL_OP_SIGN = 70, PBL_OP_SQRT = 71, PBL_OP_SQUARE = 72, PBL_OP_LOG10 = 73, PBL_OP_SIN = 74, PBL_OP_COS = 75,
   PBL_OP_TAN = 76, PBL_OP_ASIN = 77, PBL_OP_ACOS = 78, PBL_OP_ATAN = 79, PBL_OP_SINH = 80, PBL_OP_COSH = 81,
-  PBL_OP_TANH = 82, PBL_OP_ASINH = 83, PBL_OP_ACOSH = 84, PBL_OP_ATANH = 85, PBL_OP_NOT = 86
+  PBL_OP_TANH = 82, PBL_OP_ASINH = 83, PBL_OP_ACOSH = 84, PBL_OP_ATANH = 85, PBL_OP_NOT = 86,
+  /* dst <- table[(int) a]; src[1] = index into inputs[] of the table, imm[1] = its length
+   * (`self.values[idx]` of DiscreteDistribution, modeling.py:913); out of range -> nan */
+  PBL_OP_LOOKUP = 87
 } pbl_graph_op;
 
 /* Flags or-ed into pbl_graph_instr.op of a computing instruction (ppf / arithmetic / MOV) so that the

@@ -12,13 +12,14 @@ from scipy import stats
 OPS = dict(
     NOP=0, LOAD=1, STORE=2, CHECK=3, MOV=4, UNIFORM=5,
     PPF_NORM=16, PPF_UNIFORM=17, PPF_EXPON=18, PPF_TRIANG=19, PPF_GAMMA=20, PPF_LOGNORM=21,
-    PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24,
+    PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24, TABLE_INTERP=25, TABLE_SEARCH=26, TABLE_QUANTILE=27,
     ADD=32, MUL=33, SUB=34, DIV=35, POW=36, FLOORDIV=37, MOD=38, MAX=39, MIN=40, ATAN2=41, LT=42, LE=43,
     GT=44, GE=45, EQ=46, NE=47, AND=48, OR=49, ISCLOSE=50,
     NEG=64, ABS=65, LOG=66, EXP=67, FLOOR=68, CEIL=69, SIGN=70, SQRT=71, SQUARE=72, LOG10=73, SIN=74,
     COS=75, TAN=76, ASIN=77, ACOS=78, ATAN=79, SINH=80, COSH=81, TANH=82, ASINH=83, ACOSH=84, ATANH=85,
-    NOT=86,
+    NOT=86, LOOKUP=87,
 )
+QUANTILE_METHODS = ["linear", "lower", "higher", "nearest", "midpoint", "closest_observation"]
 NAME = {v: k for k, v in OPS.items()}
 
 BINARY = {
@@ -95,6 +96,25 @@ def run(program, n_slots, n, inputs, outputs, uniform=None):
                 finish(operand(ins, 0).copy())
             elif name == "UNIFORM":
                 slots[ins.dst] = uniform(ins.src[0])
+            elif name.startswith("TABLE_"):
+                if flags & 0x100:
+                    q = np.array(inputs[ins.src[0]], dtype=np.float64)
+                elif flags & 0x200:
+                    q = uniform(ins.src[0])
+                else:
+                    q = operand(ins, 0)
+                m = int(ins.imm[1])
+                tab = np.asarray(inputs[ins.src[1]])
+                if name == "TABLE_INTERP":  # CumulativeDistribution._sample, modeling.py:880-882
+                    out = np.interp(x=q, xp=tab[:m], fp=tab[m:2 * m])
+                elif name == "TABLE_SEARCH":  # DiscreteDistribution._sample, modeling.py:910-912
+                    out = np.searchsorted(tab[:m], v=q, side="right").astype(np.float64)
+                else:  # EmpiricalDistribution._sample, modeling.py:841-842
+                    out = np.quantile(a=tab[:m], q=q, method=QUANTILE_METHODS[int(ins.imm[2])])
+                finish(np.asarray(out, dtype=np.float64))
+            elif name == "LOOKUP":
+                tab = np.asarray(inputs[ins.src[1]])[: int(ins.imm[1])]
+                finish(tab[operand(ins, 0).astype(np.intp)].astype(np.float64))
             elif name.startswith("PPF_"):
                 if flags & 0x100:
                     q = np.array(inputs[ins.src[0]], dtype=np.float64)

@@ -86,6 +86,15 @@ def is_initial_sampling_node(node):
 
 
 def sample_distribution(node, q, samples):
+    name = type(node).__name__
+    if name == "EmpiricalDistribution":  # modeling.py:841-842
+        return np.quantile(a=node.data, q=q, **node.kwargs)
+    if name == "CumulativeDistribution":  # modeling.py:880-882
+        return np.interp(x=q, xp=node.q, fp=node.cumulatives)
+    if name == "DiscreteDistribution":  # modeling.py:910-913
+        idx = np.searchsorted(np.cumsum(node.probabilities), v=q, side="right")
+        return node.values[idx]
+
     def unpack(arg):
         return samples[arg] if hasattr(arg, "get_parents") else arg
 

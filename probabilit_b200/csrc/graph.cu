@@ -83,6 +83,71 @@ __device__ __noinline__ double eval_ppf(int op, double q, double p0, double p1, 
   return PBL_NAN;
 }
 
+// ---- table-lookup distributions (reference modeling.py:825-927) ----
+// np.interp(x, xp, fp) (numpy compiled_base.c arr_interp): clamp outside, exact knots return fp[j]
+__device__ __noinline__ double table_interp(double x, const double* __restrict__ t, int m) {
+  const double* xp = t;
+  const double* fp = t + m;
+  if (x != x) return x;
+  if (x >= xp[m - 1]) return fp[m - 1];
+  if (x < xp[0]) return fp[0];
+  int lo = 0, hi = m - 1;  // xp[lo] <= x < xp[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (x >= xp[mid]) lo = mid; else hi = mid;
+  }
+  if (xp[lo] == x) return fp[lo];
+  const double slope = __ddiv_rn(__dsub_rn(fp[lo + 1], fp[lo]), __dsub_rn(xp[lo + 1], xp[lo]));
+  double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xp[lo])), fp[lo]);
+  if (r != r) {
+    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xp[lo + 1])), fp[lo + 1]);
+    if (r != r && fp[lo] == fp[lo + 1]) r = fp[lo];
+  }
+  return r;
+}
+// np.searchsorted(cum, q, side="right"): the first index with cum[idx] > q
+__device__ __noinline__ double table_search_right(double q, const double* __restrict__ cum, int m) {
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cum[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return (double)lo;
+}
+// np.quantile(data, q, method=...) on sorted data (numpy/lib/_function_base_impl.py _quantile, _lerp)
+__device__ __noinline__ double table_quantile(double q, const double* __restrict__ a, int m, int method) {
+  if (q != q) return q;
+  const double n1 = (double)(m - 1);
+  const double vi = __dmul_rn(n1, q);
+  if (method == 1 || method == 2 || method == 3) {
+    double idx = method == 1 ? floor(vi) : (method == 2 ? ceil(vi) : rint(vi));
+    if (idx < 0.0) idx = 0.0;
+    if (idx > n1) idx = n1;
+    return a[(int)idx];
+  }
+  if (method == 5) {  // closest_observation: discontinuous, index from n*q - 1.5, ties to odd
+    const double index = __dadd_rn(__dadd_rn(__dmul_rn((double)m, q), -1.0), -0.5);
+    const double prev = floor(index);
+    const double gamma = index - prev;
+    double res = (gamma == 0.0 && fmod(prev, 2.0) == 1.0) ? prev : prev + 1.0;
+    if (res < 0.0) res = 0.0;
+    if (res > n1) res = n1;
+    return a[(int)res];
+  }
+  double index = vi;
+  if (method == 4) index = __dmul_rn(0.5, __dadd_rn(floor(vi), ceil(vi)));
+  double prev = floor(index), next = prev + 1.0;
+  if (index >= n1) prev = next = n1;  // _get_indexes: at / above the last element both are the last
+  if (index < 0.0) prev = next = 0.0;
+  double gamma = __dsub_rn(index, prev);
+  if (method == 4) gamma = (fmod(index, 1.0) == 0.0) ? 0.0 : 0.5;
+  const double lo = a[(int)prev], hi = a[(int)next];
+  const double diff = __dsub_rn(hi, lo);
+  double r = __dadd_rn(lo, __dmul_rn(diff, gamma));
+  if (gamma >= 0.5) r = __dsub_rn(hi, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  return r;
+}
+
 // numpy npy_divmod for doubles (numpy/_core/src/npymath/npy_math_internal.h.src)
 __device__ __forceinline__ double np_divmod(double a, double b, double* modulus) {
   double mod = fmod(a, b);
@@ -234,6 +299,11 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
           case PBL_OP_SQRT: r = __dsqrt_rn(a); break;
           case PBL_OP_SQUARE: r = __dmul_rn(a, a); break;
           case PBL_OP_NOT: r = b2d(a == 0.0); break;
+          case PBL_OP_LOOKUP: {
+            const int m = (int)in.imm[1];
+            r = (a >= 0.0 && a < (double)m) ? g.inputs[s1][(int)a] : PBL_NAN;
+            break;
+          }
           default: r = eval_unary(op, a); break;
         }
       } else if (op >= 32) {  // binary
@@ -246,6 +316,19 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
           default: r = eval_binary(op, a, b); break;
         }
       } else {  // ppf: operand 0 = q, then up to three parameters
+        if (op >= PBL_PPF_TABLE_INTERP) {  // table-lookup distributions: src[1] names a device table
+          const double* tab = g.inputs[s1];
+          const int m = (int)in.imm[1];
+          r = op == PBL_PPF_TABLE_INTERP ? table_interp(a, tab, m)
+              : (op == PBL_PPF_TABLE_SEARCH ? table_search_right(a, tab, m)
+                                            : table_quantile(a, tab, m, (int)in.imm[2]));
+          SLOT(dst) = r;
+          if (active) {
+            if ((flags & PBL_GRAPH_CHECK) && !isfinite(r)) atomicMin(g.first_nonfinite, (in.dst >> 8) & 0xFFF);
+            if (flags & PBL_GRAPH_STORE) __stcs(g.outputs[(uint32_t)in.dst >> 20] + row, r);
+          }
+          continue;
+        }
         const int s2 = in.src[2], s3 = in.src[3];
         const double p0 = s1 >= 0 ? SLOT(s1) : in.imm[1];
         const double p1 = s2 >= 0 ? SLOT(s2) : in.imm[2];
@@ -296,9 +379,11 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
     bool ok = (in.dst & 0xFF) < std::max(n_slots, 1) && in.dst >= 0;
     const bool fused_q = (in.op & (PBL_GRAPH_Q_INPUT | PBL_GRAPH_Q_UNIFORM)) != 0;
     const int nsrc = op == PBL_OP_STORE || op == PBL_OP_CHECK || op == PBL_OP_LOAD || op == PBL_OP_UNIFORM ? 0 : 4;
-    for (int s = fused_q ? 1 : 0; s < nsrc; ++s) ok = ok && in.src[s] < n_slots;
+    const bool table_op = (op >= PBL_PPF_TABLE_INTERP && op <= PBL_PPF_TABLE_QUANTILE) || op == PBL_OP_LOOKUP;
+    for (int s = fused_q ? 1 : 0; s < nsrc; ++s) ok = ok && (in.src[s] < n_slots || (table_op && s == 1));
+    if (table_op) ok = ok && in.src[1] >= 0 && in.src[1] < n_inputs && in.imm[1] >= 1.0 && in.imm[1] < 2147483647.0;
     if (op == PBL_OP_LOAD || (in.op & PBL_GRAPH_Q_INPUT)) ok = ok && in.src[0] >= 0 && in.src[0] < n_inputs;
-    if (fused_q) ok = ok && op >= PBL_PPF_NORM && op <= PBL_PPF_BERNOULLI && in.src[0] >= 0;
+    if (fused_q) ok = ok && op >= PBL_PPF_NORM && op <= PBL_PPF_TABLE_QUANTILE && in.src[0] >= 0;
     if (in.op & PBL_GRAPH_STORE) ok = ok && (int)((uint32_t)in.dst >> 20) < n_outputs && (op >= 16 || op == PBL_OP_MOV);
     if (in.op & PBL_GRAPH_CHECK) ok = ok && op >= 16;
     if (op == PBL_OP_STORE) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0 && in.src[1] < n_outputs;

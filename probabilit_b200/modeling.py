@@ -39,13 +39,14 @@ from .correlation import Cholesky, ImanConover, nearest_correlation_matrix
 OP = dict(
     NOP=0, LOAD=1, STORE=2, CHECK=3, MOV=4, UNIFORM=5,
     PPF_NORM=16, PPF_UNIFORM=17, PPF_EXPON=18, PPF_TRIANG=19, PPF_GAMMA=20, PPF_LOGNORM=21,
-    PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24,
+    PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24, TABLE_INTERP=25, TABLE_SEARCH=26, TABLE_QUANTILE=27,
     ADD=32, MUL=33, SUB=34, DIV=35, POW=36, FLOORDIV=37, MOD=38, MAX=39, MIN=40, ATAN2=41, LT=42, LE=43,
     GT=44, GE=45, EQ=46, NE=47, AND=48, OR=49, ISCLOSE=50,
     NEG=64, ABS=65, LOG=66, EXP=67, FLOOR=68, CEIL=69, SIGN=70, SQRT=71, SQUARE=72, LOG10=73, SIN=74,
     COS=75, TAN=76, ASIN=77, ACOS=78, ATAN=79, SINH=80, COSH=81, TANH=82, ASINH=83, ACOSH=84, ATANH=85,
-    NOT=86,
+    NOT=86, LOOKUP=87,
 )
+QUANTILE_METHODS = {"linear": 0, "lower": 1, "higher": 2, "nearest": 3, "midpoint": 4, "closest_observation": 5}
 MAX_SLOTS = 96
 MAX_INSTR = 4096
 
@@ -77,15 +78,19 @@ def build_corrmat(correlations):
 class _Samples:
     """Where a node's samples live: a device column, a host array, or a folded constant."""
 
-    def __init__(self, *, host=None, columns=None, index=None, dtype=None, const=None, size=None, none=False):
+    def __init__(self, *, host=None, columns=None, index=None, dtype=None, const=None, size=None, none=False,
+                 categories=None):
         self._host, self.columns, self.index, self.dtype = host, columns, index, dtype
-        self.const, self.size, self.none = const, size, none
+        self.const, self.size, self.none, self.categories = const, size, none, categories
 
     def host(self):
         if self._host is None and not self.none:
             if self.columns is not None:
                 raw = self.columns.column_to_host(self.index)
-                self._host = raw if self.dtype == _F64 else (raw != 0 if self.dtype == _BOOL else raw.astype(self.dtype))
+                if self.categories is not None:  # the device holds indices into non-numeric values
+                    self._host = self.categories[raw.astype(np.intp)]
+                else:
+                    self._host = raw if self.dtype == _F64 else (raw != 0 if self.dtype == _BOOL else raw.astype(self.dtype))
             else:
                 self._host = np.ones(self.size, dtype=self.const.dtype) * self.const[0]
         return self._host
@@ -361,6 +366,88 @@ class Distribution(AbstractDistribution):
         return OP[op], [bound[name] for name in names]
 
 
+class EmpiricalDistribution(AbstractDistribution):
+    """Inverse-CDF sampling of observed data: ``np.quantile(data, q, **kwargs)`` (reference :825-845).
+    On the device: a binary-search-free index computation on the sorted data (NumPy's quantile
+    methods linear / lower / higher / nearest / midpoint / closest_observation)."""
+
+    is_leaf = True
+
+    def __init__(self, data, **kwargs):
+        self.data = np.array(data)
+        self.kwargs = kwargs
+        super().__init__()
+
+    def __repr__(self):
+        return f"{type(self).__name__}()"
+
+    def get_parents(self):
+        yield from ()
+
+    def _table(self):
+        extra = set(self.kwargs) - {"method"}
+        method = self.kwargs.get("method", "linear")
+        if extra or method not in QUANTILE_METHODS:
+            raise NotImplementedError(f"np.quantile(**{self.kwargs}) has no device implementation "
+                                      f"(methods: {sorted(QUANTILE_METHODS)})")
+        if not np.issubdtype(self.data.dtype, np.number) or self.data.ndim != 1 or self.data.size == 0:
+            raise NotImplementedError("EmpiricalDistribution needs a non-empty 1-D numeric data array")
+        # methods without interpolation take an element of the data and keep its dtype; the others are float64
+        dtype = self.data.dtype if method in ("lower", "higher", "nearest", "closest_observation") else _F64
+        return np.sort(self.data.astype(np.float64)), QUANTILE_METHODS[method], np.dtype(dtype)
+
+
+class CumulativeDistribution(AbstractDistribution):
+    """A distribution given by points of its CDF: ``np.interp(q, quantiles, cumulatives)`` (reference :848-884)."""
+
+    is_leaf = True
+
+    def __init__(self, quantiles, cumulatives):
+        self.q = np.array(quantiles)
+        self.cumulatives = np.array(cumulatives)
+        if not np.all(np.diff(self.q) > 0):
+            raise ValueError("The quantiles must be strictly increasing.")
+        if not np.all(np.diff(self.cumulatives) > 0):
+            raise ValueError("The cumulatives must be strictly increasing.")
+        if not (np.isclose(np.min(self.q), 0) and np.isclose(np.max(self.q), 1)):
+            raise ValueError("Lowest quantile must be 0 and highest must be 1.")
+        super().__init__()
+
+    def __repr__(self):
+        return f"{type(self).__name__}(quantiles={repr(self.q)}, cumulatives={repr(self.cumulatives)})"
+
+    def get_parents(self):
+        yield from ()
+
+
+class DiscreteDistribution(AbstractDistribution):
+    """Categorical distribution: ``values[np.searchsorted(np.cumsum(p), q, side="right")]`` (reference :887-927).
+    Non-numeric values stay on the host; the device computes the category index."""
+
+    is_leaf = True
+
+    def __init__(self, values, probabilities=None):
+        self.values = np.array(values)
+        if probabilities is None:
+            self.probabilities = np.ones(len(self.values), dtype=float)
+            self.probabilities = self.probabilities / np.sum(self.probabilities)
+        else:
+            self.probabilities = np.array(probabilities)
+        if not len(self.values) == len(self.probabilities):
+            raise ValueError(f"Length mismatch: {len(self.values)=}  {len(self.probabilities)=}")
+        if not np.isclose(np.sum(self.probabilities), 1.0):
+            raise ValueError(f"Probabilities must sum to 1. {sum(self.probabilities)=}")
+        if np.any(self.probabilities < 0):
+            raise ValueError("Probabilities are not non-negative.")
+        super().__init__()
+
+    def __repr__(self):
+        return f"{type(self).__name__}(values={repr(self.values)}, probabilities={repr(self.probabilities)})"
+
+    def get_parents(self):
+        yield from ()
+
+
 class Transform(Node, OverloadMixin, abc.ABC):
     """Arithmetic on nodes (reference :933-940)."""
 
@@ -538,6 +625,7 @@ class _Emitter:
     def __init__(self):
         self.instrs = []  # [op, dst_vreg or None, [src vreg or None]*4, [imm]*4]
         self.nv = 0
+        self.table_base = 0  # index of the first lookup table in the kernel's input pointer list
 
     def imm(self, value, dtype):
         return _Val(arr=np.array([value], dtype=dtype))
@@ -585,6 +673,17 @@ class _Emitter:
         d = self._push(op, [q] + list(params))
         return _Val(vreg=d, dtype=_F64)
 
+    def table(self, op, q, table_index, length, method=0, dtype=_F64):
+        d = self._push(op, [q, 0.0, 0.0], aux=("table", table_index))
+        self.instrs[-1][3][1] = float(length)
+        self.instrs[-1][3][2] = float(method)
+        return _Val(vreg=d, dtype=dtype)
+
+    def lookup(self, idx, table_index, length, dtype):
+        d = self._push("LOOKUP", [idx, 0.0], aux=("table", table_index))
+        self.instrs[-1][3][1] = float(length)
+        return _Val(vreg=d, dtype=dtype)
+
     def raw_binary(self, dev, a, b, dtype):
         if a.is_imm and b.is_imm:
             raise AssertionError("constant sub-graphs are folded before emission")
@@ -597,7 +696,8 @@ class _Emitter:
         return np.dtype(out.dtype)
 
     def _require(self, node, dtype, vals):
-        if dtype not in (_F64, _BOOL) or any(v.dtype not in (_F64, _BOOL) and not v.is_imm for v in vals):
+        ok_in = (_F64, _BOOL, np.dtype(np.int64))
+        if dtype not in (_F64, _BOOL) or any(v.dtype not in ok_in and not v.is_imm for v in vals):
             raise NotImplementedError(
                 f"{node}: NumPy would compute this node in {dtype} from {[str(v.dtype) for v in vals]}; "
                 "the device program handles float64 and bool values (integer results only in constant sub-graphs)")
@@ -675,6 +775,8 @@ class _Emitter:
                     ins.src[0] = aux[1]
                 elif aux[0] == "col":
                     ins.src[0] = aux[1]
+                elif aux[0] == "table":
+                    ins.src[1] = self.table_base + aux[1]
                 elif aux[0] in ("store", "check"):
                     ins.src[0], ins.src[1] = slot_of[aux[1]], aux[2]
             for v in set(reads[i]):
@@ -760,13 +862,44 @@ class _GraphRun:
                 raise NotImplementedError(f"{node}: parameter {p!r} is neither a number nor a Node")
         return op, vals
 
+    def add_table(self, array):
+        self.tables.append(np.ascontiguousarray(array, dtype=np.float64))
+        return len(self.tables) - 1
+
+    def emit_distribution(self, em, node, value_of, column):
+        """One distribution node: quantile column -> inverse CDF (scipy ppf or a table lookup)."""
+        q = self.quantile(em, column[node])
+        if isinstance(node, Distribution):
+            op, params = self.parameters(node, value_of)
+            return em.ppf(op, q, params)
+        if isinstance(node, CumulativeDistribution):  # np.interp(q, self.q, self.cumulatives), reference :880-882
+            t = self.add_table(np.concatenate([node.q.astype(np.float64), node.cumulatives.astype(np.float64)]))
+            return em.table("TABLE_INTERP", q, t, len(node.q))
+        if isinstance(node, EmpiricalDistribution):  # np.quantile(self.data, q, **kwargs), reference :841-842
+            data, method, dtype = node._table()
+            return em.table("TABLE_QUANTILE", q, self.add_table(data), len(data), method, dtype=dtype)
+        # DiscreteDistribution: values[searchsorted(cumsum(p), q, "right")], reference :910-913
+        cum = np.cumsum(node.probabilities)
+        idx = em.table("TABLE_SEARCH", q, self.add_table(cum), len(cum))
+        values = node.values
+        if np.issubdtype(values.dtype, np.number) or values.dtype == np.bool_:
+            return em.lookup(idx, self.add_table(values.astype(np.float64)), len(values), values.dtype)
+        self.categories[node] = values  # non-numeric categories: the device keeps the index
+        return _Val(vreg=idx.vreg, dtype=values.dtype)
+
+    def upload_tables(self):
+        cols = [DeviceColumns.from_host(t.reshape(-1, 1)) for t in self.tables]
+        return cols, [c.column_ptr(0) for c in cols]
+
     def execute(self):
         sink, G, n = self.sink, self.G, self.size
+        self.tables, self.categories = [], {}
         members = set(sink.nodes())
         for node in members:
             node.__dict__.pop("_store", None)
+        table_kinds = (EmpiricalDistribution, CumulativeDistribution, DiscreteDistribution)
         unsupported = [m for m in members if isinstance(m, ScalarFunctionTransform) or
-                       (isinstance(m, AbstractDistribution) and not isinstance(m, Distribution))]
+                       (isinstance(m, AbstractDistribution) and not isinstance(m, (Distribution,) + table_kinds))]
         if unsupported:
             raise NotImplementedError(f"no device implementation for {unsupported[0]!r}")
 
@@ -817,9 +950,8 @@ class _GraphRun:
                 val = None if arr is None else value_of[node]
             elif node in corr_index:
                 val = em.load(("corr", corr_index[node]))
-            elif isinstance(node, Distribution):
-                op, params = self.parameters(node, value_of)
-                val = em.ppf(op, self.quantile(em, column[node]), params)
+            elif isinstance(node, AbstractDistribution):
+                val = self.emit_distribution(em, node, value_of, column)
             else:
                 val = node._emit(em, [value_of[p] for p in node.get_parents()])
             if val is None:  # NoOp: `samples_` is None (reference :993-997)
@@ -848,6 +980,9 @@ class _GraphRun:
                 ins[4] = ("in", nq + aux[1][1])
         if corr_cols is not None:
             inputs += [corr_cols.column_ptr(j) for j in range(corr_cols.k)]
+        em.table_base = len(inputs)
+        table_cols, table_ptrs = self.upload_tables()
+        inputs += table_ptrs
 
         stored = [(node, val) for node, val in keep if not val.is_imm and node not in corr_index]
         assert len(stored) == n_stored
@@ -865,7 +1000,8 @@ class _GraphRun:
             elif node in corr_index:
                 node.__dict__["_store"] = _Samples(columns=corr_cols, index=corr_index[node], dtype=val.dtype)
         for j, (node, val) in enumerate(stored):
-            node.__dict__["_store"] = _Samples(columns=out_cols, index=j, dtype=val.dtype)
+            node.__dict__["_store"] = _Samples(columns=out_cols, index=j, dtype=val.dtype,
+                                               categories=self.categories.get(node))
 
     def run_correlation(self, corr_vars, corr_index, correlations, column, folded):
         """Sample the correlated initial sampling nodes, induce the correlations
@@ -874,11 +1010,17 @@ class _GraphRun:
         em = _Emitter()
         value_of = {node: _Val(arr=arr) for node, arr in folded.items() if arr is not None}
         X = DeviceColumns(n, len(corr_vars))
+        first_table = len(self.tables)
         for j, node in enumerate(corr_vars):
-            op, params = self.parameters(node, value_of)
-            em.store(em.ppf(op, self.quantile(em, column[node]), params), j)
+            if node in self.categories or (isinstance(node, DiscreteDistribution)
+                                           and not np.issubdtype(node.values.dtype, np.number)):
+                raise ValueError(f"Cannot correlate non-numeric variable: {node}")
+            em.store(self.emit_distribution(em, node, value_of, column), j)
         inputs = [] if self.qcols is None else [self.qcols.column_ptr(j) for j in range(self.qcols.k)]
-        _run_program(em, n, 0, inputs, [X.column_ptr(j) for j in range(X.k)])
+        em.table_base = len(inputs)
+        table_cols, table_ptrs = self.upload_tables()
+        _run_program(em, n, 0, inputs + table_ptrs, [X.column_ptr(j) for j in range(X.k)])
+        del self.tables[first_table:]  # the main program registers its own tables
 
         indexed = [(tuple(corr_index[v] for v in variables), mat) for variables, mat in correlations]
         target = nearest_correlation_matrix(build_corrmat(indexed))

@@ -117,8 +117,27 @@ def correlated(ns):
     return expr, [("a", a), ("b", b), ("c", c), ("d", d), ("expr", expr)]
 
 
+def tables(ns):
+    """The table-lookup distributions (modeling.py:825-927) alone and inside arithmetic."""
+    rng = np.random.default_rng(5)
+    emp = ns.EmpiricalDistribution(rng.lognormal(size=257))
+    dice = ns.EmpiricalDistribution([1, 2, 3, 4, 5, 6], method="closest_observation")
+    low = ns.EmpiricalDistribution(rng.normal(size=50), method="lower")
+    mid = ns.EmpiricalDistribution(rng.normal(size=51), method="midpoint")
+    near = ns.EmpiricalDistribution(rng.normal(size=64), method="nearest")
+    cum = ns.CumulativeDistribution([0, 0.2, 0.8, 1], [10, 15, 20, 25])
+    disc = ns.DiscreteDistribution([10, 15, 20], probabilities=[0.2, 0.3, 0.5])
+    discf = ns.DiscreteDistribution([0.5, -1.25, 3.0, 8.0], probabilities=[0.1, 0.2, 0.3, 0.4])
+    cat = ns.DiscreteDistribution(["A", "B", "C", "D", "E", "F"])
+    noisy = ns.Distribution("norm", loc=cum, scale=0.1)
+    expr = emp + cum * 2 + disc / discf + noisy
+    sink = ns.NoOp(expr, dice, cat, low, mid, near)
+    return sink, [("emp", emp), ("dice", dice), ("low", low), ("mid", mid), ("near", near), ("cum", cum),
+                  ("disc", disc), ("discf", discf), ("cat", cat), ("noisy", noisy), ("expr", expr)]
+
+
 RECIPES = {
     "height": (height, 999), "birds": (birds, 2000), "mutual_fund": (mutual_fund, 999),
     "marginals": (marginals, 3000), "discrete": (discrete, 3000), "arithmetic": (arithmetic, 500),
-    "composite": (composite, 2000), "correlated": (correlated, 1000),
+    "composite": (composite, 2000), "correlated": (correlated, 1000), "tables": (tables, 4000),
 }

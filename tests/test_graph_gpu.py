@@ -24,12 +24,12 @@ GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_refere
 
 EXACT = {"stat", "lt", "le", "gt", "ge", "eq", "ne", "all", "any", "bool_add", "bool_mul", "floor", "ceil", "sign",
          "eggs", "survived", "p_small", "p_big", "discrete:b", "b_big", "be", "shifted", "counts", "hits", "u",
-         "sigma", "shape", "mode"}
+         "sigma", "shape", "mode", "emp", "dice", "low", "mid", "near", "cum", "disc", "discf", "cat"}
 # libm-backed transforms: CUDA's implementations are <= 2 ulp, the inputs themselves carry <= 4 ulp
 LOOSE = {"pow", "rpow", "exp", "tan", "sin", "cos", "sinh", "cosh", "tanh", "arctanh", "arccosh", "arcsinh",
          "arcsin", "arccos", "arctan", "arctan2", "log", "log10", "mod", "rmod", "floordiv", "g", "g1", "total",
          "result", "t", "x", "returns", "expr", "d", "avg", "pow2", "square", "div", "rdiv", "rate",
-         "correlated:b", "correlated:a", "correlated:c"}
+         "correlated:b", "correlated:a", "correlated:c", "noisy"}
 
 
 def ppf_device(what, q, p0=0.0, p1=0.0, p2=0.0):
