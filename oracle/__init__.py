@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
 only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it, and only as the checker / the CPU arm.
-``probabilit_b200`` never imports this package (tests/test_no_oracle_in_product.py
+``probabilit_b200`` never imports this package (tests/test_abi_cpu.py
 enforces that).
 
 Each function is a NumPy/SciPy restatement of the reference algorithm and cites

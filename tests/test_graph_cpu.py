@@ -96,3 +96,29 @@ def test_errors(monkeypatch):
         m.Distribution("cauchy").sample_from_quantiles(np.full((4, 1), 0.5))
     with pytest.raises(TypeError):
         (-(x > 0)).sample_from_quantiles(np.full((4, 1), 0.5))  # numpy: boolean negative
+
+
+def test_distribution_constructors(monkeypatch):
+    """probabilit_b200.distributions mirrors the reference's constructors (distributions.py doctests)."""
+    import probabilit_b200
+    import probabilit_b200.distributions as d
+    import probabilit_b200.modeling as m
+
+    fake_device.install(monkeypatch)
+    assert repr(d.PERT(0, 6, 10)) == 'Distribution("beta", a=3.4, b=2.6, loc=0, scale=10)'
+    assert d.pert_to_beta(0, 9, 10, gamma=6) == (6.4, 1.6, 0, 10)
+    assert repr(d.Triangular(low=1, mode=5, high=9, low_perc=0, high_perc=1)) == \
+        'Distribution("triang", loc=1, scale=8, c=0.5)'
+    loc, scale, c = d.fit_triangular_distribution(3, 8, 10, low_perc=0.10, high_perc=0.90)
+    assert abs(loc + 0.207) < 1e-2 and abs(scale - 12.53) < 1e-2 and abs(c - 0.65) < 1e-2
+    with pytest.raises(ValueError):
+        d.Triangular(5, 4, 9)
+    # Lognormal(mean, std): moments of the lognormal itself (reference distributions.py:39-45)
+    q = np.random.default_rng(0).random((20000, 1))
+    s = d.Lognormal(mean=2, std=1).sample_from_quantiles(q)
+    assert abs(s.mean() - 2.0) < 0.02 and abs(s.std() - 1.0) < 0.05
+    u = d.Uniform(2, 5).sample_from_quantiles(q)
+    assert u.min() >= 2 and u.max() < 5
+    with pytest.raises(NotImplementedError):
+        d.PERT(0, 6, 10).sample_from_quantiles(q)
+    assert probabilit_b200.Distribution is m.Distribution and probabilit_b200.PERT is d.PERT
