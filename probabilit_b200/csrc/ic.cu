@@ -18,7 +18,11 @@
 #include <cstring>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "ndtri.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pbl {
 
@@ -614,12 +618,12 @@ chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsu
     for (int i = j + 1 + tid; i < k; i += nth) W[(size_t)i * k + j] /= q;
     if (tid == 0) W[(size_t)j * k + j] = q;
     __syncthreads();
-    const int t = k - j - 1;
-    for (int idx = tid; idx < t * t; idx += nth) {
-      int ii = idx / t, mm = idx % t;
-      if (mm <= ii) {
-        size_t i = j + 1 + ii, m = j + 1 + mm;
-        W[i * k + m] -= W[i * k + j] * W[m * k + j];
+    // trailing update of the lower triangle: one warp per row i, lanes along m (coalesced, no div/mod)
+    {
+      const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+      for (int i = j + 1 + warp; i < k; i += nwarps) {
+        const double wij = W[(size_t)i * k + j];
+        for (int m = j + 1 + lane; m <= i; m += 32) W[(size_t)i * k + m] -= wij * W[(size_t)m * k + j];
       }
     }
     __syncthreads();
@@ -640,6 +644,95 @@ chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsu
       for (int i = 0; i <= c; ++i) T[(size_t)i * k + c] *= sd;
     }
   }
+}
+
+// The same computation for wide problems (k > 64), spread over the whole GPU with grid-wide barriers
+// (cooperative launch): the single-block version is bound by one SM's L2 bandwidth (k^3/3 updates
+// of an 8 MB matrix), this one by 3 grid barriers per column.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+chol_solve_grid_kernel(const double* __restrict__ G, const double* __restrict__ colsum,
+                       const double* __restrict__ P, double* __restrict__ W, double* __restrict__ T,
+                       int k, double n_total, uint32_t* __restrict__ flags, const double* __restrict__ colstd) {
+  cg::grid_group grid = cg::this_grid();
+  const int nth = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, gwarp = gt >> 5, nwarps = nth >> 5;
+  const double inv = 1.0 / (MODE == 0 ? n_total - 1.0 : n_total);
+  for (int e = gt; e < k * k; e += nth) {
+    int i = e / k, j = e % k;
+    W[e] = (G[e] - colsum[i] * colsum[j] / n_total) * inv;
+  }
+  grid.sync();
+  if (MODE == 0) {
+    for (int i = gt; i < k; i += nth) T[i] = sqrt(W[(size_t)i * k + i]);
+    grid.sync();
+    for (int e = gt; e < k * k; e += nth) {
+      int i = e / k, j = e % k;
+      double c = W[e] / T[i];
+      c = c / T[j];
+      W[e] = (c != c) ? c : fmin(fmax(c, -1.0), 1.0);
+    }
+    grid.sync();
+  }
+  for (int j = 0; j < k; ++j) {
+    const double d = W[(size_t)j * k + j];  // identical in every thread: a consistent early exit
+    if (!(d > 0.0)) {
+      if (gt == 0) flags[kFlagNotPD] = 1u;
+      for (int e = gt; e < k * k; e += nth) T[e] = 0.0;
+      return;
+    }
+    const double q = sqrt(d);
+    grid.sync();  // everybody has read the pivot
+    for (int i = j + 1 + gt; i < k; i += nth) W[(size_t)i * k + j] /= q;
+    if (gt == 0) W[(size_t)j * k + j] = q;
+    grid.sync();
+    for (int i = j + 1 + gwarp; i < k; i += nwarps) {
+      const double wij = W[(size_t)i * k + j];
+      for (int m = j + 1 + lane; m <= i; m += 32) W[(size_t)i * k + m] -= wij * W[(size_t)m * k + j];
+    }
+    grid.sync();
+  }
+  // T = Q^-T P^T by back substitution, one thread per column of T
+  for (int c = gt; c < k; c += nth) {
+    for (int i = k - 1; i >= 0; --i) {
+      if (i > c) {
+        T[(size_t)i * k + c] = 0.0;
+        continue;
+      }
+      double s = P[(size_t)c * k + i];
+      for (int m = i + 1; m <= c; ++m) s -= W[(size_t)m * k + i] * T[(size_t)m * k + c];
+      T[(size_t)i * k + c] = s / W[(size_t)i * k + i];
+    }
+    if (MODE == 1) {
+      const double sd = colstd[c];
+      for (int i = 0; i <= c; ++i) T[(size_t)i * k + c] *= sd;
+    }
+  }
+}
+
+template <int MODE>
+int launch_chol_solve(IcPlan* p, double n_total, const double* colstd, cudaStream_t stream) {
+  if (p->k <= 64) {
+    chol_solve_kernel<MODE><<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, p->k, n_total,
+                                                   p->flags, colstd);
+    PBL_LAUNCH_CHECK();
+    return kOk;
+  }
+  int k = p->k;
+  const double* G = p->gram;
+  const double* cs = p->colsum;
+  const double* P = p->P;
+  double* W = p->work;
+  double* T = p->T;
+  uint32_t* fl = p->flags;
+  void* args[] = {&G, &cs, &P, &W, &T, &k, &n_total, &fl, &colstd};
+  int per_sm = 0;
+  PBL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_solve_grid_kernel<MODE>, 256, 0));
+  const int blocks = std::max(1, std::min(per_sm, 2) * num_sms());
+  PBL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)chol_solve_grid_kernel<MODE>, dim3(blocks), dim3(256), args, 0,
+                                             stream));
+  PBL_LAUNCH_CHECK();
+  return kOk;
 }
 
 // ======================================================================================
@@ -999,9 +1092,7 @@ int ic_stage_solve(IcPlan* p, int64_t n_total, cudaStream_t stream) {
     set_last_error("ic: set_target has not been called");
     return kBadShape;
   }
-  chol_solve_kernel<0><<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, p->k,
-                                             (double)n_total, p->flags, nullptr);
-  PBL_LAUNCH_CHECK();
+  PBL_RETURN_IF(launch_chol_solve<0>(p, (double)n_total, nullptr, stream));
   return kOk;
 }
 
@@ -1082,8 +1173,7 @@ int cholesky_correlator_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs
   standardise_kernel<<<dim3(rb, k), 256, 0, stream>>>(X, xrs, xcs, n, mean, sd, p->scores);
   PBL_LAUNCH_CHECK();
   PBL_RETURN_IF(ic_stage_gram(p, stream));
-  chol_solve_kernel<1><<<1, 256, 0, stream>>>(p->gram, p->colsum, p->P, p->work, p->T, k, (double)n, p->flags, sd);
-  PBL_LAUNCH_CHECK();
+  PBL_RETURN_IF(launch_chol_solve<1>(p, (double)n, sd, stream));
   PBL_RETURN_IF(ic_stage_transform(p, stream));
   add_mean_kernel<<<dim3(rb, k), 256, 0, stream>>>(p->scores, n, mean, Y, yrs, ycs);
   PBL_LAUNCH_CHECK();

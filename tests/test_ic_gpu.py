@@ -299,3 +299,25 @@ def test_full_size_properties():
     # rho_s = 6/pi * asin(rho/2)
     want = 6.0 / np.pi * np.arcsin(Ct / 2.0)
     assert np.max(np.abs(spearman - want)) < 5e-3, np.max(np.abs(spearman - want))
+
+
+@pytest.mark.parametrize("n,k", [(3000, 100), (2500, 257)])
+def test_wide_problem_uses_grid_cholesky(n, k):
+    """k > 64: correlation / Cholesky / T are computed by the cooperative multi-block kernel."""
+    from probabilit_b200 import Cholesky, ImanConover
+
+    rng = np.random.default_rng(21)
+    X = np.asfortranarray(rng.normal(size=(n, k)))
+    C = random_target(rng, k)
+    ref = oic.iman_conover_stages(X, C)
+    got = gpu_util.run_stages(X, C)
+    assert got["status"] == 0
+    np.testing.assert_allclose(got["T"], ref["T"], rtol=0, atol=1e-10)
+    np.testing.assert_array_equal(got["result"], ref["result"])
+    np.testing.assert_array_equal(ImanConover().set_target(C)(X), oic.iman_conover(X, C))
+    np.testing.assert_allclose(Cholesky().set_target(C)(X), oic.cholesky_correlator(X, C), rtol=1e-10, atol=1e-10)
+    # perfectly collinear scores -> not positive definite, detected consistently by every block
+    Xd = X.copy()
+    Xd[:, 1] = Xd[:, 0]
+    with pytest.raises(ValueError, match="not positive definite"):
+        ImanConover().set_target(C)(Xd)
