@@ -8,6 +8,8 @@ The reference is single-process; this is the B200-native s
     1. all-to-all  rows -> columns : rank g receives its columns C_g at full length N = G*n_local
     2. rank_scores on C_g          : sort, tie-run average ranks, van der Waerden scores (:394-395)
     3. all-to-all  columns -> rows : every rank gets the scores of its rows, all K columns
+       (1-3 and 6-8 are pipelined per local column: the exchange of column r+1 and the return of
+       column r-1 overlap the sort of column r)
     4. local Gram + column sums, NCCL all-reduce of the (K*K + K) doubles   (np.corrcoef, :398)
     5. solve (replicated, K x K) and transform of the local rows            (:398-414)
     6. all-to-all  rows -> columns of the correlated scores
@@ -75,10 +77,11 @@ class CudaStages:
             if p is not None:
                 _lib.check(self.lib.pbl_ic_stage_begin(p.handle, self._stream()))
 
-    def rank_scores(self):  # x_cols -> scores_cols (+ sortedX kept inside the sort plan)
-        if self.kc:
+    def rank_scores(self, ci=0, nci=None):  # x_cols -> scores_cols (+ sortedX kept inside the sort plan)
+        nci = self.kc - ci if nci is None else nci
+        if nci > 0:
             _lib.check(self.lib.pbl_ic_stage_rank_scores(
-                self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, 0, self.kc, self._stream()))
+                self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
 
     def gram_partial(self):  # scores_rows -> gram, colsum (local partial sums)
         _lib.check(self.lib.pbl_ic_stage_gram(self.row_plan.handle, self._stream()))
@@ -87,10 +90,11 @@ class CudaStages:
         _lib.check(self.lib.pbl_ic_stage_solve(self.row_plan.handle, self.n_total, self._stream()))
         _lib.check(self.lib.pbl_ic_stage_transform(self.row_plan.handle, self._stream()))
 
-    def rank_gather(self):  # scores_cols (correlated) -> y_cols
-        if self.kc:
+    def rank_gather(self, ci=0, nci=None):  # scores_cols (correlated) -> y_cols
+        nci = self.kc - ci if nci is None else nci
+        if nci > 0:
             _lib.check(self.lib.pbl_ic_stage_rank_gather(
-                self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, 0, self.kc, self._stream()))
+                self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
 
     def status(self):
         st = 0
@@ -131,49 +135,55 @@ class DistributedImanConover:
         self.st = stages
 
     # ------------------------------------------------------------------ exchanges
-    def _exchange(self, ops_send, ops_recv):
-        """ops_*: lists of (tensor, peer); matched pairwise per peer in list order."""
-        dist = self.dist
-        reqs = []
-        p2p = []
-        for t, peer in ops_recv:
-            p2p.append(dist.P2POp(dist.irecv, t, peer))
-        for t, peer in ops_send:
-            p2p.append(dist.P2POp(dist.isend, t, peer))
-        if p2p:
-            reqs = dist.batch_isend_irecv(p2p)
+    # A transpose is done in ROUNDS: in round r every rank g exchanges what belongs to its r-th local
+    # column, so that the sort of local column r can start as soon as its own round has landed while
+    # the later rounds are still in flight (NCCL runs them on its own stream), and the scores of
+    # column r travel back while column r+1 is being sorted.  With kc columns per rank the exposed
+    # communication is ~1/kc of a bulk transpose.
+    def _round(self, r, rows_buf, cols_buf, to_cols):
+        """Issue round r of a transpose (asynchronously); returns the requests to wait on.
+        to_cols: rows_buf [K][n_local] -> cols_buf [kc][n_total]; else the reverse."""
+        dist, nl = self.dist, self.n_local
+        ops = []
+        mine = r < self.kc
+        for g, (a, b) in enumerate(self.blocks):
+            theirs = r < b - a
+            if g == self.rank:
+                if mine:
+                    if to_cols:
+                        cols_buf[r, g * nl:(g + 1) * nl].copy_(rows_buf[self.c0 + r])
+                    else:
+                        rows_buf[self.c0 + r].copy_(cols_buf[r, g * nl:(g + 1) * nl])
+                continue
+            if to_cols:
+                if mine:
+                    ops.append(dist.P2POp(dist.irecv, cols_buf[r, g * nl:(g + 1) * nl], g))
+                if theirs:
+                    ops.append(dist.P2POp(dist.isend, rows_buf[a + r], g))
+            else:
+                if theirs:
+                    ops.append(dist.P2POp(dist.irecv, rows_buf[a + r], g))
+                if mine:
+                    ops.append(dist.P2POp(dist.isend, cols_buf[r, g * nl:(g + 1) * nl], g))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def _wait(reqs):
         for r in reqs:
             r.wait()
 
+    @property
+    def rounds(self):
+        return max(b - a for a, b in self.blocks)
+
     def rows_to_cols(self, rows_buf, cols_buf):
-        """rows_buf [K][n_local] (this rank's rows) -> cols_buf [kc][n_total] (this rank's columns)."""
-        nl = self.n_local
-        send, recv = [], []
-        for g, (a, b) in enumerate(self.blocks):
-            if g == self.rank:
-                continue
-            for c in range(a, b):
-                send.append((rows_buf[c], g))
-            for ci in range(self.kc):
-                recv.append((cols_buf[ci, g * nl:(g + 1) * nl], g))
-        for ci in range(self.kc):
-            cols_buf[ci, self.rank * nl:(self.rank + 1) * nl].copy_(rows_buf[self.c0 + ci])
-        self._exchange(send, recv)
+        """Bulk form (all rounds, then wait)."""
+        for r in range(self.rounds):
+            self._wait(self._round(r, rows_buf, cols_buf, True))
 
     def cols_to_rows(self, cols_buf, rows_buf):
-        """cols_buf [kc][n_total] -> rows_buf [K][n_local]."""
-        nl = self.n_local
-        send, recv = [], []
-        for g, (a, b) in enumerate(self.blocks):
-            if g == self.rank:
-                continue
-            for ci in range(self.kc):
-                send.append((cols_buf[ci, g * nl:(g + 1) * nl], g))
-            for c in range(a, b):
-                recv.append((rows_buf[c], g))
-        for ci in range(self.kc):
-            rows_buf[self.c0 + ci].copy_(cols_buf[ci, self.rank * nl:(self.rank + 1) * nl])
-        self._exchange(send, recv)
+        for r in range(self.rounds):
+            self._wait(self._round(r, cols_buf=cols_buf, rows_buf=rows_buf, to_cols=False))
 
     # ------------------------------------------------------------------ the transform
     def run(self, X_local, Y_local):
@@ -183,18 +193,35 @@ class DistributedImanConover:
         Xc = X_local.T  # [K][n_local] view of the column-major storage
         Yc = Y_local.T
         assert Xc.is_contiguous() and Yc.is_contiguous(), "X_local / Y_local must be column-major"
+        R = self.rounds
         for _attempt in range(2):
             st.begin()
-            self.rows_to_cols(Xc, st.x_cols)                 # 1
-            st.rank_scores()                                 # 2
-            self.cols_to_rows(st.scores_cols, st.scores_rows)  # 3
+            # 1-3: X rows -> columns, rank + score each column, scores columns -> rows, pipelined
+            pending = self._round(0, Xc, st.x_cols, True)
+            back = []
+            for r in range(R):
+                self._wait(pending)
+                pending = self._round(r + 1, Xc, st.x_cols, True) if r + 1 < R else []
+                if r < self.kc:
+                    st.rank_scores(r, 1)
+                back.append(self._round(r, st.scores_rows, st.scores_cols, False))
+            for reqs in back:
+                self._wait(reqs)
             st.gram_partial()                                # 4
             dist.all_reduce(st.gram)
             dist.all_reduce(st.colsum)
             st.solve_and_transform()                         # 5
-            self.rows_to_cols(st.scores_rows, st.scores_cols)  # 6
-            st.rank_gather()                                 # 7
-            self.cols_to_rows(st.y_cols, Yc)                 # 8
+            # 6-8: correlated scores rows -> columns, rank + gather, Y columns -> rows, pipelined
+            pending = self._round(0, st.scores_rows, st.scores_cols, True)
+            back = []
+            for r in range(R):
+                self._wait(pending)
+                pending = self._round(r + 1, st.scores_rows, st.scores_cols, True) if r + 1 < R else []
+                if r < self.kc:
+                    st.rank_gather(r, 1)
+                back.append(self._round(r, Yc, st.y_cols, False))
+            for reqs in back:
+                self._wait(reqs)
             status = self._agree(st.status())
             if status != 6:  # PBL_RETRY: some rank switched to the exact 64-bit sort; run again
                 break

@@ -34,11 +34,14 @@ class NumpyStages:
     def begin(self):
         self._status = 0
 
-    def rank_scores(self):
+    def rank_scores(self, ci=0, nci=None):
         from scipy.special import ndtri
+        nci = self.kc - ci if nci is None else nci
         x = self.x_cols.numpy()
-        self.sortedX = np.sort(x, axis=1)
-        for c in range(self.kc):
+        if self.sortedX is None:
+            self.sortedX = np.empty_like(x)
+        for c in range(ci, ci + nci):
+            self.sortedX[c] = np.sort(x[c])
             r, _ = oic.average_ranks(x[c])
             self.scores_cols[c] = torch.from_numpy(ndtri(r / (self.n_total + 1)))
 
@@ -62,12 +65,11 @@ class NumpyStages:
         s = self.scores_rows.numpy()
         self.scores_rows.copy_(torch.from_numpy((s.T @ T).T.copy()))
 
-    def rank_gather(self):
+    def rank_gather(self, ci=0, nci=None):
+        nci = self.kc - ci if nci is None else nci
         corr = self.scores_cols.numpy()
-        out = np.empty_like(corr)
-        for c in range(self.kc):
-            out[c] = self.sortedX[c][oic.midpoint_index(corr[c])]
-        self.y_cols.copy_(torch.from_numpy(out))
+        for c in range(ci, ci + nci):
+            self.y_cols[c] = torch.from_numpy(self.sortedX[c][oic.midpoint_index(corr[c])])
 
     def status(self):
         return self._status
