@@ -108,6 +108,13 @@ PBL_API int pbl_permcorr_steps(pbl_ic_plan* plan, double* Y_dev, const int32_t* 
                                void* stream);
 PBL_API int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr);
 
+/* Verification helper: np.corrcoef(X, rowvar=False) (spearman == 0) or the Spearman matrix
+ * (Pearson correlation of scipy.stats.rankdata's average ranks; the Spearman mode of CorrelationMatrix,
+ * correlation.py:835-837) of device-resident X into HOST out[k*k].  Spearman needs a plan with sort
+ * workspace.  Synchronous. */
+PBL_API int pbl_corrcoef_f64(pbl_ic_plan* plan, const double* X_dev, int64_t x_row_stride, int64_t x_col_stride,
+                             int32_t spearman, double* out, void* stream);
+
 /* ImanConover.__call__ with HOST buffers on a reusable plan: X / Y contiguous in C or F order, the
  * caller provides device staging for n*k doubles each.  For column-major data the host<->device
  * copies are pipelined with the per-column sorts (page-locked host memory makes them asynchronous). */

@@ -357,6 +357,33 @@ class Cholesky(_PlanCorrelator):
         _raise_for_status(st)
 
 
+def corrcoef(X, *, spearman=False, device=None):
+    """``np.corrcoef(X, rowvar=False)`` or (``spearman=True``) the Spearman rank-correlation matrix of
+    an (N, K) matrix, computed on the GPU: X may be a NumPy array, a CUDA ``torch.Tensor`` or
+    ``DeviceColumns`` (no host traffic).  Lets the Pearson / Spearman acceptance checks of the
+    correlators (reference tests/test_permutation_correlator.py) run at N = 1e8."""
+    from ._device import DeviceColumns, as_device_columns
+
+    lib = _lib.require_gpu()
+    if _is_cuda_tensor(X):
+        N, K = X.shape
+        ptr, rs, cs, keep = X.data_ptr(), X.stride(0), X.stride(1), X
+        device = X.device.index if device is None else device
+    else:
+        cols, keep = as_device_columns(X)
+        N, K, ptr, rs, cs = cols.n, cols.k, cols.ptr, 1, cols.n
+    plan = _IcPlan(N, K, 0 if device is None else int(device), rows_only=not spearman)
+    try:
+        out = np.empty((K, K))
+        st = _lib.check(lib.pbl_corrcoef_f64(plan.handle, C.c_void_p(ptr), rs, cs, 1 if spearman else 0,
+                                             out.ctypes.data, None), "pbl_corrcoef_f64")
+        _raise_for_status(st)
+    finally:
+        plan.close()
+    del keep
+    return out
+
+
 class SwapIndexGenerator:
     """Disjoint swap index pairs drawn from a NumPy generator exactly like the reference's
     (correlation.py:428-470): consumes one ``rng.permutation(n)`` 2*size entries at a time and

@@ -142,6 +142,12 @@ int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr) {
   return pbl::permcorr_read_corr(plan->impl, corr);
 }
 
+int pbl_corrcoef_f64(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, int32_t spearman, double* out,
+                     void* stream) {
+  if (!plan || !X || !out) return kBadShape;
+  return pbl::corrcoef_run(plan->impl, X, xrs, xcs, spearman, out, (cudaStream_t)stream);
+}
+
 static bool contiguous_layout(int64_t n, int32_t k, int64_t rs, int64_t cs) {
   return (rs == 1 && cs == n) || (cs == 1 && rs == k) || (n == 1 && cs == 1) || (k == 1 && rs == 1);
 }

@@ -1315,6 +1315,51 @@ int centre_columns(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, const d
   return kOk;
 }
 
+__global__ void corr_from_gram_kernel(const double* __restrict__ G, int k, double* __restrict__ R) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k * k; e += gridDim.x * blockDim.x) {
+    const int i = e / k, j = e % k;
+    double c = G[e] / sqrt(G[(size_t)i * k + i]);
+    c = c / sqrt(G[(size_t)j * k + j]);
+    R[e] = (c != c) ? c : fmin(fmax(c, -1.0), 1.0);
+  }
+}
+
+// np.corrcoef(X, rowvar=False) (spearman == 0) or the Spearman rank correlation matrix
+// (scipy.stats.spearmanr: Pearson correlation of the average ranks) of device-resident X, written to
+// host memory.  Verification helper: lets the acceptance checks of the correlators run on the device
+// at sizes the host cannot hold.  Uses plan->scores (and the sort workspace for Spearman).
+int corrcoef_run(IcPlan* p, const double* X, int64_t xrs, int64_t xcs, int spearman, double* out_host,
+                 cudaStream_t stream) {
+  const int k = p->k;
+  const int64_t n = p->n;
+  if (!p->moments) {
+    PBL_CUDA_CHECK(cudaMalloc((void**)&p->moments, ((size_t)2 * k + (size_t)k * kMomBlocks) * 8));
+    p->bytes += ((size_t)2 * k + (size_t)k * kMomBlocks) * 8;
+  }
+  double* mean = p->moments;
+  PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
+  const double* basis = X;
+  int64_t brs = xrs, bcs = xcs;
+  if (spearman) {
+    if (p->rows_only) {
+      set_last_error("corrcoef: the Spearman mode needs a plan with a sort workspace");
+      return kBadShape;
+    }
+    PBL_RETURN_IF(ic_stage_rank_scores(p, X, xrs, xcs, 0, k, stream, /*ranks_only=*/true));
+    basis = p->scores;
+    brs = 1;
+    bcs = n;
+  }
+  PBL_RETURN_IF(column_moments(p, basis, brs, bcs, nullptr, mean, 0, stream));
+  PBL_RETURN_IF(centre_columns(p, basis, brs, bcs, mean, p->scores, stream));
+  PBL_RETURN_IF(ic_stage_gram(p, stream));
+  corr_from_gram_kernel<<<std::min(64, (k * k + 255) / 256), 256, 0, stream>>>(p->gram, k, p->work);
+  PBL_LAUNCH_CHECK();
+  PBL_CUDA_CHECK(cudaMemcpyAsync(out_host, p->work, (size_t)k * k * 8, cudaMemcpyDeviceToHost, stream));
+  int st = ic_read_status(p, stream);
+  return st == kRetry ? corrcoef_run(p, X, xrs, xcs, spearman, out_host, stream) : st;
+}
+
 int ic_read_status(IcPlan* p, cudaStream_t stream) {
   uint32_t h[8];
   PBL_CUDA_CHECK(cudaMemcpyAsync(h, p->flags, sizeof(h), cudaMemcpyDeviceToHost, stream));

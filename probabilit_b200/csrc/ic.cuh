@@ -82,6 +82,9 @@ int permcorr_steps(IcPlan* plan, double* Y, const int32_t* step_col, const int32
                    int64_t errors_cap, int64_t* n_errors, cudaStream_t stream);
 int permcorr_read_corr(IcPlan* plan, double* corr_host);
 
+int corrcoef_run(IcPlan* plan, const double* X, int64_t xrs, int64_t xcs, int spearman, double* out_host,
+                 cudaStream_t stream);
+
 // Cholesky correlator (reference correlation.py:205-285); synchronous like ic_plan_run.
 int cholesky_correlator_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
                             double* Y, int64_t y_row_stride, int64_t y_col_stride, cudaStream_t stream);

@@ -285,16 +285,10 @@ def test_full_size_properties():
         del a, b
     print("entries per column that differ from a permutation (tie-runs of the correlated scores):", mismatches)
     assert max(mismatches) <= 16 and sum(mismatches) <= 64, mismatches
-    # Spearman correlation of Y = Pearson correlation of its ranks
-    R = torch.empty((d, n), dtype=torch.float64, device="cuda")
-    for c in range(d):
-        order = torch.argsort(Y[:, c])
-        R[c, order] = torch.arange(n, dtype=torch.float64, device="cuda")
-        del order
-    R -= R.mean(dim=1, keepdim=True)
-    cov = (R @ R.T) / n
-    sd = torch.sqrt(torch.diag(cov))
-    spearman = (cov / sd[:, None] / sd[None, :]).cpu().numpy()
+    # Spearman matrix of the result, on the device (pbl_corrcoef_f64)
+    from probabilit_b200.correlation import corrcoef
+
+    spearman = corrcoef(Y, spearman=True)
     # the induced rank correlation matches the target's rank correlation: for normal scores
     # rho_s = 6/pi * asin(rho/2)
     want = 6.0 / np.pi * np.arcsin(Ct / 2.0)
@@ -321,3 +315,14 @@ def test_wide_problem_uses_grid_cholesky(n, k):
     Xd[:, 1] = Xd[:, 0]
     with pytest.raises(ValueError, match="not positive definite"):
         ImanConover().set_target(C)(Xd)
+
+
+def test_device_corrcoef_pearson_and_spearman():
+    """pbl_corrcoef_f64 against np.corrcoef / scipy.stats.spearmanr (1e-12), incl. ties."""
+    from probabilit_b200.correlation import corrcoef
+
+    rng = np.random.default_rng(30)
+    X = rng.normal(size=(20_000, 5)) @ rng.normal(size=(5, 5))
+    X[:, 2] = rng.poisson(4.0, 20_000)
+    np.testing.assert_allclose(corrcoef(X), np.corrcoef(X, rowvar=False), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(corrcoef(X, spearman=True), sp.stats.spearmanr(X).statistic, rtol=0, atol=1e-12)
