@@ -218,6 +218,11 @@ typedef enum pbl_graph_op {
    *   TABLE_QUANTILE np.quantile(sorted data, q, method), table = data[m]    (EmpiricalDistribution)
    *                  method 0 linear 1 lower 2 higher 3 nearest 4 midpoint 5 closest_observation */
   PBL_PPF_TABLE_INTERP = 25, PBL_PPF_TABLE_SEARCH = 26, PBL_PPF_TABLE_QUANTILE = 27,
+  /* four-parameter distributions: operands (q, a, b, scale), result for loc = 0 -- the caller adds loc
+   * with a separate PBL_OP_ADD (scipy's `_ppf * scale + loc` is two roundings anyway)
+   *   BETA      scipy.stats.beta(a, b)       (PERT, reference src/probabilit/distributions.py:79-94)
+   *   TRUNCNORM scipy.stats.truncnorm(a, b)  (TruncatedNormal, distributions.py:17-29) */
+  PBL_PPF_BETA = 28, PBL_PPF_TRUNCNORM = 29,
   /* binary (dst <- op(a, b)) */
   PBL_OP_ADD = 32, PBL_OP_MUL = 33, PBL_OP_SUB = 34, PBL_OP_DIV = 35, PBL_OP_POW = 36, PBL_OP_FLOORDIV = 37,
   PBL_OP_MOD = 38, PBL_OP_MAX = 39, PBL_OP_MIN = 40, PBL_OP_ATAN2 = 41, PBL_OP_LT = 42, PBL_OP_LE = 43,

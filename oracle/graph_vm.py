@@ -13,6 +13,7 @@ OPS = dict(
     NOP=0, LOAD=1, STORE=2, CHECK=3, MOV=4, UNIFORM=5,
     PPF_NORM=16, PPF_UNIFORM=17, PPF_EXPON=18, PPF_TRIANG=19, PPF_GAMMA=20, PPF_LOGNORM=21,
     PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24, TABLE_INTERP=25, TABLE_SEARCH=26, TABLE_QUANTILE=27,
+    PPF_BETA=28, PPF_TRUNCNORM=29,
     ADD=32, MUL=33, SUB=34, DIV=35, POW=36, FLOORDIV=37, MOD=38, MAX=39, MIN=40, ATAN2=41, LT=42, LE=43,
     GT=44, GE=45, EQ=46, NE=47, AND=48, OR=49, ISCLOSE=50,
     NEG=64, ABS=65, LOG=66, EXP=67, FLOOR=68, CEIL=69, SIGN=70, SQRT=71, SQUARE=72, LOG10=73, SIN=74,
@@ -58,6 +59,10 @@ def ppf(name, q, p):
             return stats.binom(p[0], p[1], loc=p[2]).ppf(q)
         if name == "PPF_BERNOULLI":
             return stats.bernoulli(p[0], loc=p[1]).ppf(q)
+        if name == "PPF_BETA":  # operands (a, b, scale); loc is added by the next instruction
+            return stats.beta(p[0], p[1], scale=p[2]).ppf(q)
+        if name == "PPF_TRUNCNORM":
+            return stats.truncnorm(p[0], p[1], scale=p[2]).ppf(q)
     raise ValueError(name)
 
 

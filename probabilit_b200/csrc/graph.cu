@@ -83,6 +83,14 @@ __device__ __noinline__ double eval_ppf(int op, double q, double p0, double p1, 
   return PBL_NAN;
 }
 
+// four-parameter distributions: (a, b, loc, scale)
+__device__ __noinline__ double eval_ppf4(int op, double q, double a, double b, double loc, double scale) {
+  if (op == PBL_PPF_BETA)
+    return ppf_continuous(q, a > 0.0 && b > 0.0, 0.0, 1.0, loc, scale, [&] { return ibeta_inv(a, b, q); });
+  // truncnorm: support [a, b] in standard units, scipy argcheck a < b
+  return ppf_continuous(q, a < b, a, b, loc, scale, [&] { return truncnorm_ppf_core(q, a, b); });
+}
+
 // ---- table-lookup distributions (reference modeling.py:825-927) ----
 // np.interp(x, xp, fp) (numpy compiled_base.c arr_interp): clamp outside, exact knots return fp[j]
 __device__ __noinline__ double table_interp(double x, const double* __restrict__ t, int m) {
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
           default: r = eval_binary(op, a, b); break;
         }
       } else {  // ppf: operand 0 = q, then up to three parameters
-        if (op >= PBL_PPF_TABLE_INTERP) {  // table-lookup distributions: src[1] names a device table
+        if (op >= PBL_PPF_TABLE_INTERP && op <= PBL_PPF_TABLE_QUANTILE) {  // table lookups: src[1] names a device table
           const double* tab = g.inputs[s1];
           const int m = (int)in.imm[1];
           r = op == PBL_PPF_TABLE_INTERP ? table_interp(a, tab, m)
@@ -335,6 +343,8 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
         const double p2 = s3 >= 0 ? SLOT(s3) : in.imm[3];
         if (op == PBL_PPF_NORM) {  // the common case stays inline
           r = ppf_continuous(a, true, -kInf, kInf, p0, p1, [&] { return ndtri(a); });
+        } else if (op >= PBL_PPF_BETA) {  // (q, a, b, scale); the host adds loc with a separate ADD
+          r = eval_ppf4(op, a, p0, p1, 0.0, p2);
         } else {
           r = eval_ppf(op, a, p0, p1, p2);
         }
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(kGraphBlock) graph_eval_kernel(const GraphArgs
 __global__ void __launch_bounds__(256) ppf_kernel(int what, const double* __restrict__ q, int64_t n, double p0,
                                                   double p1, double p2, double* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
-    out[i] = eval_ppf(what, q[i], p0, p1, p2);
+    out[i] = what >= PBL_PPF_BETA ? eval_ppf4(what, q[i], p0, p1, 0.0, p2) : eval_ppf(what, q[i], p0, p1, p2);
 }
 
 }  // namespace
@@ -383,7 +393,7 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
     for (int s = fused_q ? 1 : 0; s < nsrc; ++s) ok = ok && (in.src[s] < n_slots || (table_op && s == 1));
     if (table_op) ok = ok && in.src[1] >= 0 && in.src[1] < n_inputs && in.imm[1] >= 1.0 && in.imm[1] < 2147483647.0;
     if (op == PBL_OP_LOAD || (in.op & PBL_GRAPH_Q_INPUT)) ok = ok && in.src[0] >= 0 && in.src[0] < n_inputs;
-    if (fused_q) ok = ok && op >= PBL_PPF_NORM && op <= PBL_PPF_TABLE_QUANTILE && in.src[0] >= 0;
+    if (fused_q) ok = ok && op >= PBL_PPF_NORM && op <= PBL_PPF_TRUNCNORM && in.src[0] >= 0;
     if (in.op & PBL_GRAPH_STORE) ok = ok && (int)((uint32_t)in.dst >> 20) < n_outputs && (op >= 16 || op == PBL_OP_MOV);
     if (in.op & PBL_GRAPH_CHECK) ok = ok && op >= 16;
     if (op == PBL_OP_STORE) ok = ok && in.src[0] >= 0 && in.src[0] < n_slots && in.src[1] >= 0 && in.src[1] < n_outputs;
@@ -438,7 +448,8 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
 
 int pbl_ppf_f64(int32_t what, const double* q_dev, int64_t n, double p0, double p1, double p2, double* out_dev,
                 void* stream) {
-  if (n < 0 || (n > 0 && (!q_dev || !out_dev)) || what < PBL_PPF_NORM || what > PBL_PPF_BERNOULLI) {
+  if (n < 0 || (n > 0 && (!q_dev || !out_dev)) || what < PBL_PPF_NORM || what > PBL_PPF_TRUNCNORM ||
+      (what >= PBL_PPF_TABLE_INTERP && what <= PBL_PPF_TABLE_QUANTILE)) {
     pbl::set_last_error("pbl_ppf_f64: bad arguments");
     return kBadShape;
   }

@@ -253,6 +253,116 @@ __device__ __noinline__ double igami(double a, double p) {
   return x;
 }
 
+// ---- regularised incomplete beta I_x(a, b) and its inverse (beta.ppf -> PERT,
+//      reference src/probabilit/distributions.py:79-94; scipy: Boost ibeta_inv) ----
+// Continued fraction of DLMF 8.17.22 evaluated with the modified Lentz algorithm.
+__device__ __noinline__ double betacf(double a, double b, double x) {
+  const double tiny = 1e-300;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < tiny) d = tiny;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 2000; ++m) {
+    const double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) <= 2.0 * kMachEp) break;
+  }
+  return h;
+}
+// returns I_x(a, b); *comp receives 1 - I_x(a, b) computed without cancellation
+__device__ __noinline__ double ibeta(double a, double b, double x, double* comp) {
+  if (x <= 0.0) { *comp = 1.0; return 0.0; }
+  if (x >= 1.0) { *comp = 0.0; return 1.0; }
+  const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+  const double front = exp(a * log(x) + b * log1p(-x) - lbeta);
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    const double v = front * betacf(a, b, x) / a;
+    *comp = 1.0 - v;
+    return v;
+  }
+  const double v = front * betacf(b, a, 1.0 - x) / b;
+  *comp = v;
+  return 1.0 - v;
+}
+// scipy.special.betaincinv(a, b, p): safeguarded Newton / Halley on I_x(a, b) - p inside a bracket
+// (on the complement for p > 1/2), starting from the Abramowitz-Stegun 26.5.22 approximation.
+__device__ __noinline__ double ibeta_inv(double a, double b, double p) {
+  if (a != a || b != b || p != p || !(a > 0.0) || !(b > 0.0) || p < 0.0 || p > 1.0) return PBL_NAN;
+  if (p == 0.0) return 0.0;
+  if (p == 1.0) return 1.0;
+  double x;
+  if (a >= 1.0 && b >= 1.0) {
+    const double pp = p < 0.5 ? p : 1.0 - p;
+    const double t = sqrt(-2.0 * log(pp));
+    double y = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
+    if (p < 0.5) y = -y;
+    const double al = (y * y - 3.0) / 6.0;
+    const double h = 2.0 / (1.0 / (2.0 * a - 1.0) + 1.0 / (2.0 * b - 1.0));
+    const double w = y * sqrt(al + h) / h - (1.0 / (2.0 * b - 1.0) - 1.0 / (2.0 * a - 1.0)) * (al + 5.0 / 6.0 - 2.0 / (3.0 * h));
+    x = a / (a + b * exp(2.0 * w));
+  } else {
+    const double lna = log(a / (a + b)), lnb = log(b / (a + b));
+    const double t = exp(a * lna) / a, u = exp(b * lnb) / b;
+    const double w = t + u;
+    x = p < t / w ? pow(a * w * p, 1.0 / a) : 1.0 - pow(b * w * (1.0 - p), 1.0 / b);
+  }
+  if (!(x > 0.0)) x = 1e-300;
+  if (!(x < 1.0)) x = 1.0 - kMachEp;
+  const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+  const bool upper = p > 0.5;
+  const double q = 1.0 - p;
+  double lo = 0.0, hi = 1.0;
+  for (int it = 0; it < 60; ++it) {
+    double comp;
+    const double v = ibeta(a, b, x, &comp);
+    const double err = upper ? (q - comp) : (v - p);  // > 0: x too large
+    if (err == 0.0) break;
+    if (err > 0.0) hi = x; else lo = x;
+    const double pdf = exp((a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta);
+    double xn = x;
+    if (pdf > 0.0 && !isinf(pdf)) {
+      const double u = err / pdf;
+      const double g = (a - 1.0) / x - (b - 1.0) / (1.0 - x);  // pdf' / pdf
+      double den = 1.0 - 0.5 * u * g;
+      if (!(den > 0.5)) den = 0.5;  // keep the Halley correction bounded
+      xn = x - u / den;
+    }
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);  // left the bracket: bisect
+    const double dx = fabs(xn - x);
+    x = xn;
+    if (dx <= 2.0 * kMachEp * x) break;
+  }
+  return x;
+}
+
+// ---- truncated normal (truncnorm.ppf, reference distributions.py:17-29) ----
+// Phi and 1 - Phi through erfc (accurate in relative terms in both tails); the quantile is taken on
+// the side where the truncated mass is computed without cancellation.
+__device__ __noinline__ double truncnorm_ppf_core(double q, double a, double b) {
+  const double rs2 = 0.70710678118654752440;
+  if (a < 0.0) {  // work with the lower tails
+    const double Fa = 0.5 * erfc(-a * rs2), Fb = 0.5 * erfc(-b * rs2);
+    return ndtri(Fa + q * (Fb - Fa));
+  }
+  const double Sa = 0.5 * erfc(a * rs2), Sb = 0.5 * erfc(b * rs2);  // upper tails
+  return -ndtri(Sb + (1.0 - q) * (Sa - Sb));
+}
+
 // log of the Poisson pmf at integer k
 __device__ __forceinline__ double poisson_logpmf(double k, double mu) {
   return k * log(mu) - mu - lgamma(k + 1.0);

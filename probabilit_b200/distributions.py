@@ -2,9 +2,9 @@
 ``Distribution`` of probabilit_b200.modeling.  They only compute scipy parameters on the host (control
 plane); sampling runs in the fused graph kernel.
 
-``PERT`` (beta) and ``TruncatedNormal`` (truncnorm) build the same ``Distribution`` objects as the
-reference, but their inverse CDFs are not among the device opcodes yet (SURVEY.md section 8f ranks them
-"next"): sampling them raises ``NotImplementedError`` instead of silently running on the CPU.
+``PERT`` (beta) and ``TruncatedNormal`` (truncnorm) map onto the four-parameter device opcodes
+(PBL_PPF_BETA / PBL_PPF_TRUNCNORM, csrc/special.cuh: safeguarded Halley on the incomplete beta, erfc-based
+truncated-normal quantile).
 """
 import warnings
 

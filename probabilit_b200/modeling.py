@@ -40,6 +40,7 @@ OP = dict(
     NOP=0, LOAD=1, STORE=2, CHECK=3, MOV=4, UNIFORM=5,
     PPF_NORM=16, PPF_UNIFORM=17, PPF_EXPON=18, PPF_TRIANG=19, PPF_GAMMA=20, PPF_LOGNORM=21,
     PPF_POISSON=22, PPF_BINOM=23, PPF_BERNOULLI=24, TABLE_INTERP=25, TABLE_SEARCH=26, TABLE_QUANTILE=27,
+    PPF_BETA=28, PPF_TRUNCNORM=29,
     ADD=32, MUL=33, SUB=34, DIV=35, POW=36, FLOORDIV=37, MOD=38, MAX=39, MIN=40, ATAN2=41, LT=42, LE=43,
     GT=44, GE=45, EQ=46, NE=47, AND=48, OR=49, ISCLOSE=50,
     NEG=64, ABS=65, LOG=66, EXP=67, FLOOR=68, CEIL=69, SIGN=70, SQRT=71, SQUARE=72, LOG10=73, SIN=74,
@@ -313,6 +314,9 @@ _DISTRIBUTIONS = {
     "poisson": ("PPF_POISSON", ("mu",), False),
     "binom": ("PPF_BINOM", ("n", "p"), False),
     "bernoulli": ("PPF_BERNOULLI", ("p",), False),
+    # four-parameter ones: the device op takes (q, a, b, scale); loc is added by a separate ADD
+    "beta": ("PPF_BETA", ("a", "b"), True),
+    "truncnorm": ("PPF_TRUNCNORM", ("a", "b"), True),
 }
 
 
@@ -871,6 +875,10 @@ class _GraphRun:
         q = self.quantile(em, column[node])
         if isinstance(node, Distribution):
             op, params = self.parameters(node, value_of)
+            if op in (OP["PPF_BETA"], OP["PPF_TRUNCNORM"]):  # (a, b, loc, scale) -> op(q, a, b, scale) + loc
+                a, b, loc, scale = params
+                core = em.ppf(op, q, [a, b, scale])
+                return em.raw_binary("ADD", core, loc, _F64)
             return em.ppf(op, q, params)
         if isinstance(node, CumulativeDistribution):  # np.interp(q, self.q, self.cumulatives), reference :880-882
             t = self.add_table(np.concatenate([node.q.astype(np.float64), node.cumulatives.astype(np.float64)]))

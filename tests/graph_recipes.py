@@ -136,8 +136,19 @@ def tables(ns):
                   ("disc", disc), ("discf", discf), ("cat", cat), ("noisy", noisy), ("expr", expr)]
 
 
+def four_param(ns):
+    """beta (PERT) and truncnorm: the four-parameter inverse CDFs."""
+    pert = ns.Distribution("beta", a=3.4, b=2.6, loc=0, scale=10)
+    small = ns.Distribution("beta", a=0.6, b=0.8, loc=-1, scale=2)
+    tn = ns.Distribution("truncnorm", a=-1.5, b=2.0, loc=3.0, scale=0.5)
+    tail = ns.Distribution("truncnorm", a=2.5, b=6.0)
+    total = pert + small + tn + tail
+    return total, [("pert", pert), ("small", small), ("tn", tn), ("tail", tail), ("total", total)]
+
+
 RECIPES = {
     "height": (height, 999), "birds": (birds, 2000), "mutual_fund": (mutual_fund, 999),
     "marginals": (marginals, 3000), "discrete": (discrete, 3000), "arithmetic": (arithmetic, 500),
     "composite": (composite, 2000), "correlated": (correlated, 1000), "tables": (tables, 4000),
+    "four_param": (four_param, 3000),
 }

@@ -119,6 +119,8 @@ def test_distribution_constructors(monkeypatch):
     assert abs(s.mean() - 2.0) < 0.02 and abs(s.std() - 1.0) < 0.05
     u = d.Uniform(2, 5).sample_from_quantiles(q)
     assert u.min() >= 2 and u.max() < 5
-    with pytest.raises(NotImplementedError):
-        d.PERT(0, 6, 10).sample_from_quantiles(q)
+    pert = d.PERT(0, 6, 10).sample_from_quantiles(q)  # beta inverse CDF
+    assert 0 <= pert.min() and pert.max() <= 10 and abs(pert.mean() - (0 + 4 * 6 + 10) / 6) < 0.05
+    tn = d.TruncatedNormal(loc=3, scale=0.5, low=2.5, high=4).sample_from_quantiles(q)
+    assert tn.min() >= 2.5 and tn.max() <= 4
     assert probabilit_b200.Distribution is m.Distribution and probabilit_b200.PERT is d.PERT
