@@ -213,8 +213,11 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"Iman-Conover fp64 N={args.n} d={d} mixed norm/triang/gamma marginals "
-                               "(BASELINE.json configs[2])", "cpu_rows_per_step": n_ref},
+        "config": {"workload": f"Iman-Conover fp64 N={args.n} rows per GPU, d={d}, mixed norm/triang/gamma "
+                               "marginals (BASELINE.json configs[2]), pseudo-random uniforms",
+                   "rows_per_gpu": args.n, "d": d, "cpu_rows_per_step": n_ref,
+                   "note": "the reference's NumPy/SciPy path (oracle port) on the host cores; each step is a "
+                           "bounded row sample of the workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
