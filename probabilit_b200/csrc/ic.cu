@@ -491,9 +491,9 @@ gram_kernel(const double* __restrict__ S, int64_t n, int k, double* __restrict__
     for (int r = rg; r < R; r += RG) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sI[(4 * ti + i) * LD + r];
+      for (int i = 0; i < 4; ++i) a[i] = sI[(ti + TG * i) * LD + r];  // columns interleaved by TG: the TG
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sJ[(4 * tj + j) * LD + r];
+      for (int j = 0; j < 4; ++j) b[j] = sJ[(tj + TG * j) * LD + r];  // threads of a row hit distinct banks
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -535,8 +535,8 @@ gram_kernel(const double* __restrict__ S, int64_t n, int k, double* __restrict__
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[(4 * ti + i) * CT + 4 * tj + j] = acc[i][j];
-      if (tj == 0) out[CT * CT + 4 * ti + i] = sum[i];
+      for (int j = 0; j < 4; ++j) out[(ti + TG * i) * CT + tj + TG * j] = acc[i][j];
+      if (tj == 0) out[CT * CT + ti + TG * i] = sum[i];
     }
   }
 }

@@ -66,3 +66,19 @@ def test_errors():
         PermutationCorrelator(seed=0).set_target(np.array([[1, 0.5], [0.5, 1]]))(X)
     with pytest.raises(ValueError):
         PermutationCorrelator(iterations=-1)
+
+
+def test_infinite_iterations_stop_on_tolerance():
+    """iterations=0 means 'until tol' in the reference (correlation.py:644-646): the device loop runs
+    chunk after chunk and stops at the same step as the oracle."""
+    from probabilit_b200 import PermutationCorrelator
+
+    rng = np.random.default_rng(17)
+    X = rng.normal(size=(400, 3))
+    Ct = np.array([[1, 0.4, 0.1], [0.4, 1, 0.3], [0.1, 0.3, 1]])
+    want = op.permutation_correlator(X, Ct, iterations=0, tol=0.02, seed=2)
+    pc = PermutationCorrelator(iterations=0, tol=0.02, seed=2).set_target(Ct)
+    pc._CHUNK_STEPS = 300
+    got = pc(X)
+    np.testing.assert_array_equal(got, want)
+    assert pc._error(np.corrcoef(got, rowvar=False), Ct) < 0.02
