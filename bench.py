@@ -176,7 +176,7 @@ def time_graph(n, lib):
     for _ in range(20):
         returns = returns * m.Distribution("norm", loc=1.11, scale=0.15) + 1200
     best = float("inf")
-    for rep in range(4):
+    for rep in range(6):
         run = m._GraphRun(returns, m._PhiloxSource(rep, n, 20), "imanconover", [])
         lib.pbl_stream_synchronize(None)
         t0 = time.perf_counter()
