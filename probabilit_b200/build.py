@@ -50,6 +50,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     exe = nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("PBL_EXTRA_NVCC_FLAGS", "").split()  # developer instrumentation (e.g. -DPBL_PASS_PROFILE)
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")

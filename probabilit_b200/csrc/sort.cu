@@ -305,6 +305,18 @@ __device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t
   *reinterpret_cast<uint32_t*>(addr) = v;
 }
 
+#ifdef PBL_PASS_PROFILE
+// developer instrumentation (tools/pass_phases.py): cycle stamps of every 64th tile at the phase boundaries
+__device__ long long g_pass_stamps[8][8192];
+__device__ unsigned int g_pass_stamp_count;
+#define PBL_STAMP(i)                                                                                  \
+  do {                                                                                                \
+    if (threadIdx.x == 0 && stamp_slot >= 0) g_pass_stamps[i][stamp_slot] = clock64();                \
+  } while (0)
+#else
+#define PBL_STAMP(i)
+#endif
+
 struct PassSmem {
   uint64_t* big;      // [TILE] 8-byte member
   uint32_t* small_;   // [TILE] 4-byte member
@@ -317,7 +329,7 @@ struct PassSmem {
 template <int BLOCK, int ITEMS, bool SCATTER, bool FULL>
 __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm, const int col,
                                           const uint32_t tile, const uint32_t nvalid, const int src,
-                                          const int dst, const uint32_t dshift, const KeyMap& map) {
+                                          const int dst, const uint32_t dshift, const KeyMap& map, const int stamp_slot) {
   using Key = typename PassTypes<SCATTER>::Key;
   using Val = typename PassTypes<SCATTER>::Val;
   constexpr int TILE = BLOCK * ITEMS;
@@ -382,6 +394,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(wh_addr + dig[u] * 4u), "r"(1u) : "memory");
   }
   __syncthreads();
+  PBL_STAMP(2);
 
   // ---- per bin: exclusive scan over warps, tile total; publish it for the tiles behind us as
   //      early as possible, then exclusive scan over bins ----
@@ -420,6 +433,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
       if ((uint32_t)w < warp) bin_start += sm.wsum[w];
     sm.bstart[tid] = bin_start;
   }
+  PBL_STAMP(3);
 
   // ---- rank inside the warp.  Three phases so that the ITEMS chains overlap instead of
   //      serialising: (1) the mask of lanes holding the same digit, built from 8 ballots (one
@@ -469,6 +483,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
       rank[u] = __shfl_sync(0xFFFFFFFFu, rank[u], 31 - __clz(m[u])) + __popc(m[u] & lt);
   }
   __syncthreads();  // bin starts visible to everyone
+  PBL_STAMP(4);
 
   // ---- scatter to shared memory in digit order ----
 #pragma unroll
@@ -497,6 +512,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
     for (int u = 0; u < ITEMS; ++u) s_vals[rank[u]] = v[u];
   }
 
+  PBL_STAMP(5);
   // ---- exclusive prefix of this bin over all earlier tiles (they published long ago) ----
   if (tid < kRadix) {
     uint32_t excl = 0;
@@ -546,6 +562,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
     sm.goff[tid] = base + excl - bin_start;  // + position in tile order = global slot
   }
   __syncthreads();
+  PBL_STAMP(6);
 
   // ---- coalesced runs out to HBM ----
   uint64_t* out_big = (dst == 1 ? a.keysA : a.keysB) + (size_t)col * n;
@@ -566,6 +583,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, const PassSmem& sm,
       }
     }
   }
+  PBL_STAMP(7);
 }
 
 template <int BLOCK, int ITEMS, int MINB, bool SCATTER>
@@ -605,15 +623,31 @@ partition_pass_kernel(const PassArgs a) {
     map = load_key_map(a.kminmax, col, a.window_bits);
     dshift = map.sh + (uint32_t)a.pass * kRadixBits;
   }
+  int stamp_slot = -1;
+#ifdef PBL_PASS_PROFILE
+  const long long t_entry = clock64();
+#endif
   if (tid == 0) *s_tile = atomicAdd(&a.tile_counter[col], 1u);
   for (int i = tid; i < NWARPS * kRadix; i += BLOCK) sm.hist[i] = 0;
   __syncthreads();
   const uint32_t tile = *s_tile;
+#ifdef PBL_PASS_PROFILE
+  if (tid == 0) {
+    if ((tile & 63u) == 17u && !SCATTER && a.pass == 1) {
+      stamp_slot = (int)atomicAdd(&g_pass_stamp_count, 1u);
+      if (stamp_slot >= 8192) stamp_slot = -1;
+    }
+    if (stamp_slot >= 0) {
+      g_pass_stamps[0][stamp_slot] = t_entry;
+      g_pass_stamps[1][stamp_slot] = clock64();
+    }
+  }
+#endif
   const uint32_t nvalid = min((uint32_t)TILE, a.n - tile * (uint32_t)TILE);
   if (nvalid == (uint32_t)TILE)
-    pass_body<BLOCK, ITEMS, SCATTER, true>(a, sm, col, tile, nvalid, src, dst, dshift, map);
+    pass_body<BLOCK, ITEMS, SCATTER, true>(a, sm, col, tile, nvalid, src, dst, dshift, map, stamp_slot);
   else
-    pass_body<BLOCK, ITEMS, SCATTER, false>(a, sm, col, tile, nvalid, src, dst, dshift, map);
+    pass_body<BLOCK, ITEMS, SCATTER, false>(a, sm, col, tile, nvalid, src, dst, dshift, map, stamp_slot);
 }
 
 // Second half of the scatter: out[row] = value for (row, value) pairs that are already grouped by
@@ -711,6 +745,21 @@ bool g_profile = false;
 std::vector<PassEvent> g_events;
 
 }  // namespace
+
+#ifdef PBL_PASS_PROFILE
+}  // namespace pbl
+extern "C" __attribute__((visibility("default"))) int pbl_debug_pass_stamps(long long* out, int cap) {
+  unsigned int cnt = 0;
+  cudaMemcpyFromSymbol(&cnt, pbl::g_pass_stamp_count, sizeof(cnt));
+  int take = (int)std::min<unsigned int>(cnt, (unsigned int)std::min(cap, 8192));
+  for (int i = 0; i < 8; ++i)
+    cudaMemcpyFromSymbol(out + (size_t)i * cap, pbl::g_pass_stamps, (size_t)take * 8, (size_t)i * 8192 * 8);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(pbl::g_pass_stamp_count, &zero, sizeof(zero));
+  return take;
+}
+namespace pbl {
+#endif
 
 void sort_profile_enable(bool on) { g_profile = on; }
 
