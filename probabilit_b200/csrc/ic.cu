@@ -541,6 +541,117 @@ gram_kernel(const double* __restrict__ S, int64_t n, int k, double* __restrict__
   }
 }
 
+// k <= 16 (one 16 x 16 tile, HBM-bound): same thread grid and partial layout as gram_kernel<4>, but
+// (a) the rows of the next step travel HBM -> shared memory with cp.async while the current step is
+// multiplied (double buffer, no registers held by loads in flight), and (b) every shared-memory
+// read fetches two adjacent rows of a column (LDS.128): 8 loads per 32 FMAs.  The two row groups of
+// a warp sit 8 rows apart (16 banks), which keeps the 8 distinct 16-byte reads of a warp on
+// distinct banks.
+constexpr int kGramSmallRows = 128;
+__global__ void __launch_bounds__(256, 3)
+gram_small_kernel(const double* __restrict__ S, int64_t n, int k, double* __restrict__ partials,
+                  int nrb, int64_t rows_per_block) {
+  constexpr int TG = 4, CT = 16, R = kGramSmallRows, LD = R + 2, PER = CT * R / 256;  // 8 elements per thread and step
+  __shared__ __align__(16) double sbuf[2][CT * LD];
+  const int tid = threadIdx.x;
+  const int rg = tid / (TG * TG);
+  const int tt = tid % (TG * TG);
+  const int ti = tt / TG, tj = tt % TG;
+  const int rbase = (rg & 1) * 8 + (rg >> 1) * 16;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(n, r_begin + rows_per_block);
+  const int lr = tid % R, lc = tid / R;  // element e of a step: column 2 e + lc, row lr
+
+  double acc[4][4];
+  double sum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sum[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  }
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(&sbuf[0][0]) + (uint32_t)(lc * LD + lr) * 8u;
+  auto issue = [&](int buf, int64_t r0) {  // rows past the end are zero-filled (src-size 0)
+    const int64_t row = r0 + lr;
+    const bool row_ok = row < r_end;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const int c = 2 * e + lc;
+      const bool ok = row_ok && c < k;
+      const double* src = ok ? S + (int64_t)c * n + row : S;
+      const uint32_t dst = s_base + (uint32_t)(buf * CT * LD + 2 * e * LD) * 8u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(ok ? 8 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0, r_begin);
+  int buf = 0;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += R, buf ^= 1) {
+    issue(buf ^ 1, r0 + R);  // that buffer was released by the barrier that ended the previous step
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const double* sI = sbuf[buf];
+#pragma unroll
+    for (int pq = 0; pq < 4; ++pq) {
+      const int r = rbase + 2 * pq;
+      double2 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(&sI[(ti + TG * i) * LD + r]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(&sI[(tj + TG * j) * LD + r]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fma(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fma(a[i].y, b[j].y, acc[i][j]);
+        }
+      if (tj == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          sum[i] += a[i].x;
+          sum[i] += a[i].y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // fold the 16 row groups in a fixed order
+  double* red = sbuf[0];  // [TG*TG][20]
+  for (int g = 1; g < 256 / (TG * TG); ++g) {
+    if (rg == g) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[tt * 20 + i * 4 + j] = acc[i][j];
+        red[tt * 20 + 16 + i] = sum[i];
+      }
+    }
+    __syncthreads();
+    if (rg == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += red[tt * 20 + i * 4 + j];
+        sum[i] += red[tt * 20 + 16 + i];
+      }
+    }
+    __syncthreads();
+  }
+  if (rg == 0) {
+    double* out = partials + (size_t)blockIdx.x * (CT * CT + CT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[(ti + TG * i) * CT + tj + TG * j] = acc[i][j];
+      if (tj == 0) out[CT * CT + ti + TG * i] = sum[i];
+    }
+  }
+}
+
 __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nrb, int k, int CT,
                                    double* __restrict__ gram, double* __restrict__ colsum) {
   const int nt = (k + CT - 1) / CT;
@@ -815,13 +926,27 @@ transform_small_kernel(double* __restrict__ S, int64_t n, int k, const double* _
   double acc[KMAX];
 #pragma unroll
   for (int c = 0; c < KMAX; ++c) acc[c] = 0.0;
+  if (KMAX <= 16) {
+    // the whole row is fetched before the first store: the in-place stores may alias later loads
+    // as far as the compiler can tell, so interleaving them would serialise KMAX HBM round trips
+    double s[KMAX];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) {
-    if (j < k) {
-      const double sj = S[(int64_t)j * n + r];
+    for (int j = 0; j < KMAX; ++j) s[j] = (j < k) ? __ldcs(S + (int64_t)j * n + r) : 0.0;
 #pragma unroll
-      for (int c = j; c < KMAX; ++c) acc[c] = fma(sj, sT[j * KMAX + c], acc[c]);
-      S[(int64_t)j * n + r] = acc[j];
+    for (int j = 0; j < KMAX; ++j) {
+#pragma unroll
+      for (int c = j; c < KMAX; ++c) acc[c] = fma(s[j], sT[j * KMAX + c], acc[c]);
+      if (j < k) S[(int64_t)j * n + r] = acc[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      if (j < k) {
+        const double sj = S[(int64_t)j * n + r];
+#pragma unroll
+        for (int c = j; c < KMAX; ++c) acc[c] = fma(sj, sT[j * KMAX + c], acc[c]);
+        S[(int64_t)j * n + r] = acc[j];
+      }
     }
   }
 }
@@ -957,8 +1082,9 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
   const int CT = 4 * p->gram_tg;
   const int nt = (k + CT - 1) / CT;
   const int npairs = nt * (nt + 1) / 2;
-  int64_t max_rb = (n + kGramRows - 1) / kGramRows;
-  int want = std::max(1, (4 * num_sms() + npairs - 1) / npairs);
+  int64_t max_rb = (n + kGramSmallRows - 1) / kGramSmallRows;
+  // whole waves: gram_small_kernel runs 3 blocks per SM, gram_kernel 4
+  int want = std::max(1, ((p->gram_tg == 4 ? 3 : 4) * num_sms() + npairs - 1) / npairs);
   p->gram_row_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_rb, want));
   A(&p->gram_partials, (size_t)npairs * p->gram_row_blocks * (CT * CT + CT));
   if (rc != kOk) {
@@ -1063,12 +1189,13 @@ int ic_stage_gram(IcPlan* p, cudaStream_t stream) {
   const int npairs = nt * (nt + 1) / 2;
   const int nrb = p->gram_row_blocks;
   int64_t rows_per = (p->n + nrb - 1) / nrb;
-  rows_per = (rows_per + kGramRows - 1) / kGramRows * kGramRows;
+  const int step_rows = TG == 4 ? kGramSmallRows : kGramRows;
+  rows_per = (rows_per + step_rows - 1) / step_rows * step_rows;
   dim3 grid((unsigned)nrb, (unsigned)npairs);
   size_t smem = (size_t)2 * CT * (kGramRows + 1) * 8;
   smem = std::max(smem, (size_t)TG * TG * 20 * 8);
-  if (TG == 4)
-    gram_kernel<4><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
+  if (TG == 4)  // k <= 16: one tile pair
+    gram_small_kernel<<<(unsigned)nrb, 256, 0, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
   else if (TG == 8)
     gram_kernel<8><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
   else {

@@ -34,33 +34,68 @@ __global__ void minmax_init_kernel(uint64_t* __restrict__ kminmax, int ncols) {
   }
 }
 
+// Order-preserving 32-bit image of the HIGH word of an fp64 (sign, exponent, top 20 mantissa bits):
+// monotone (not strictly) in the value, NaNs land beyond the infinities on either side.
+__device__ __forceinline__ uint32_t hi_image(uint32_t hi32) {
+  return hi32 ^ ((uint32_t)((int32_t)hi32 >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t hi_image_of(double d) { return hi_image((uint32_t)__double2hiint(d)); }
+
 template <int BLOCK, int UNROLL>
 __global__ void __launch_bounds__(BLOCK)
 col_minmax_kernel(const double* __restrict__ raw, int64_t row_stride, int64_t col_stride, uint32_t n,
                   uint64_t* __restrict__ kminmax, uint32_t* __restrict__ error_flag) {
-  // tracked as doubles (one fmin / fmax each; 64-bit integer min/max cost ~5 ALU instructions on a
-  // part whose integer pipe is the bottleneck) and converted to keys once per block
+  // The four extremes are tracked exactly as doubles per thread, but an element only reaches that
+  // code (several emulated fp64 min/max, ~45 instructions) when a 32-bit FILTER on the image of its
+  // high word says it could move one of them: outside [f_min, f_max] of what the warp has seen, or
+  // inside the gap [f_neg, f_pos] between the warp's largest negative and smallest positive value.
+  // The filters are shared by the warp and refreshed after every exact update, so after the first
+  // few batches an element costs 2 + 4 integer instructions (records are O(log n) per warp).
+  // Zeros, infinities and NaNs always pass the filter.
   __shared__ double s_lo[BLOCK / 32], s_hi[BLOCK / 32], s_nm[BLOCK / 32], s_pm[BLOCK / 32];
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
   const int col = blockIdx.y;
   const double* colp = raw + (int64_t)col * col_stride;
   double lo = inf, hi = -inf, negmax = -inf, posmin = inf;  // fmin / fmax drop NaNs
   bool saw_nan = false;
+  uint32_t f_min = 0xFFFFFFFFu, f_max = 0u, f_neg = 0u, f_pos = 0xFFFFFFFFu;  // everything passes
   const uint64_t step = (uint64_t)gridDim.x * BLOCK * UNROLL;
   for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n; base += step) {
     double d[UNROLL];
+    if (base + (uint64_t)BLOCK * UNROLL <= n) {  // interior batch: no bounds tests
+      const double* p0 = colp + (int64_t)(base + threadIdx.x) * row_stride;
+      const int64_t du = (int64_t)BLOCK * row_stride;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      uint64_t i = base + (uint64_t)u * BLOCK + threadIdx.x;
-      d[u] = (i < n) ? ld_stream_f64(colp + (int64_t)i * row_stride) : colp[0];
+      for (int u = 0; u < UNROLL; ++u) d[u] = ld_stream_f64(p0 + u * du);
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        uint64_t i = base + (uint64_t)u * BLOCK + threadIdx.x;
+        d[u] = (i < n) ? ld_stream_f64(colp + (int64_t)i * row_stride) : colp[0];
+      }
     }
+    bool pass = false;
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      saw_nan |= (d[u] != d[u]);
-      lo = fmin(lo, d[u]);
-      hi = fmax(hi, d[u]);
-      negmax = fmax(negmax, d[u] < 0.0 ? d[u] : -inf);
-      posmin = fmin(posmin, d[u] > 0.0 ? d[u] : inf);
+      const uint32_t h = hi_image_of(d[u]);
+      pass |= (h <= f_min) | (h >= f_max) | ((h >= f_neg) & (h <= f_pos));
+    }
+    if (__any_sync(0xFFFFFFFFu, pass)) {
+      if (pass) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          saw_nan |= (d[u] != d[u]);
+          lo = fmin(lo, d[u]);
+          hi = fmax(hi, d[u]);
+          negmax = fmax(negmax, d[u] < 0.0 ? d[u] : -inf);
+          posmin = fmin(posmin, d[u] > 0.0 ? d[u] : inf);
+        }
+      }
+      // (a lane without candidates contributes its neutral starting values)
+      f_min = __reduce_min_sync(0xFFFFFFFFu, hi_image_of(lo));
+      f_max = __reduce_max_sync(0xFFFFFFFFu, hi_image_of(hi));
+      f_neg = __reduce_max_sync(0xFFFFFFFFu, hi_image_of(negmax));
+      f_pos = __reduce_min_sync(0xFFFFFFFFu, hi_image_of(posmin));
     }
   }
 #pragma unroll
