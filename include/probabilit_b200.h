@@ -57,6 +57,19 @@ PBL_API int pbl_memcpy_h2d(void* dst_dev, const void* src, uint64_t bytes, void*
 PBL_API int pbl_memcpy_d2h(void* dst, const void* src_dev, uint64_t bytes, void* stream);
 PBL_API int pbl_stream_synchronize(void* stream);
 
+/* ---- peer memory (one process per GPU, NVLink): the multi-GPU Iman-Conover moves its row <-> column
+ * transposes with the copy engines straight into / out of the peers' buffers.  The reference is
+ * single-process (no counterpart).  export: 64-byte CUDA IPC handle of a buffer that is the BASE of a
+ * device allocation made by this library (pbl_device_malloc, pbl_ic_plan_buffer 0/1); open: map a
+ * peer's buffer into this process (peer access is enabled on first use); copy_many: `count`
+ * device-to-device copies (local or peer pointers) issued on a pool of side streams, ordered after
+ * the work already in `stream`, which resumes when all of them have finished. ---- */
+PBL_API int pbl_ipc_export(const void* ptr_dev, void* handle64);
+PBL_API int pbl_ipc_open(const void* handle64, void** ptr_dev);
+PBL_API int pbl_ipc_close(void* ptr_dev);
+PBL_API int pbl_peer_copy_many(int32_t count, void* const* dst_dev, const void* const* src_dev,
+                               const uint64_t* bytes, void* stream);
+
 /* ---- Iman-Conover correlator: ImanConover().set_target(C)(X), correlation.py:288-425 ---- */
 typedef struct pbl_ic_plan pbl_ic_plan;
 

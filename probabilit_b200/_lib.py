@@ -38,6 +38,10 @@ SIGNATURES = {
     "pbl_memcpy_h2d": (C.c_int, [_vp, _vp, _u64, _vp]),
     "pbl_memcpy_d2h": (C.c_int, [_vp, _vp, _u64, _vp]),
     "pbl_stream_synchronize": (C.c_int, [_vp]),
+    "pbl_ipc_export": (C.c_int, [_vp, _vp]),
+    "pbl_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "pbl_ipc_close": (C.c_int, [_vp]),
+    "pbl_peer_copy_many": (C.c_int, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp]),
     "pbl_ic_plan_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_vp)]),
     "pbl_ic_plan_create_ex": (C.c_int, [_i64, _i32, _i32, _i32, C.POINTER(_vp)]),
     "pbl_ic_plan_destroy": (C.c_int, [_vp]),

@@ -75,6 +75,66 @@ int pbl_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream) {
   PBL_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return kOk;
 }
+// ---- peer memory over NVLink (multi-GPU transposes, probabilit_b200/distributed.py) ----
+int pbl_ipc_export(const void* ptr_dev, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+  cudaIpcMemHandle_t h;
+  PBL_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr_dev)));
+  memcpy(handle64, &h, sizeof(h));
+  return kOk;
+}
+int pbl_ipc_open(const void* handle64, void** ptr_dev) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  PBL_CUDA_CHECK(cudaIpcOpenMemHandle(ptr_dev, h, cudaIpcMemLazyEnablePeerAccess));
+  return kOk;
+}
+int pbl_ipc_close(void* ptr_dev) {
+  PBL_CUDA_CHECK(cudaIpcCloseMemHandle(ptr_dev));
+  return kOk;
+}
+
+namespace {
+constexpr int kCopyStreams = 4;
+struct CopyPool {
+  bool ready = false;
+  cudaStream_t s[kCopyStreams];
+  cudaEvent_t fork, join[kCopyStreams];
+};
+CopyPool g_copy_pool[64];
+}  // namespace
+
+// `count` device-to-device copies (local or peer-mapped pointers, any mix), spread over a small
+// pool of side streams so that several copy engines / NVLink ports work at once; ordered after
+// everything already in `stream`, and `stream` continues after all of them.
+int pbl_peer_copy_many(int32_t count, void* const* dst, const void* const* src, const uint64_t* bytes,
+                       void* stream) {
+  int dev = 0;
+  PBL_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return kBadShape;
+  CopyPool& cp = g_copy_pool[dev];
+  if (!cp.ready) {
+    PBL_CUDA_CHECK(cudaEventCreateWithFlags(&cp.fork, cudaEventDisableTiming));
+    for (int i = 0; i < kCopyStreams; ++i) {
+      PBL_CUDA_CHECK(cudaStreamCreateWithFlags(&cp.s[i], cudaStreamNonBlocking));
+      PBL_CUDA_CHECK(cudaEventCreateWithFlags(&cp.join[i], cudaEventDisableTiming));
+    }
+    cp.ready = true;
+  }
+  cudaStream_t main = (cudaStream_t)stream;
+  const int used = count < kCopyStreams ? count : kCopyStreams;
+  PBL_CUDA_CHECK(cudaEventRecord(cp.fork, main));
+  for (int i = 0; i < used; ++i) PBL_CUDA_CHECK(cudaStreamWaitEvent(cp.s[i], cp.fork, 0));
+  for (int i = 0; i < count; ++i)
+    if (bytes[i])
+      PBL_CUDA_CHECK(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, cp.s[i % kCopyStreams]));
+  for (int i = 0; i < used; ++i) {
+    PBL_CUDA_CHECK(cudaEventRecord(cp.join[i], cp.s[i]));
+    PBL_CUDA_CHECK(cudaStreamWaitEvent(main, cp.join[i], 0));
+  }
+  return kOk;
+}
+
 int pbl_stream_synchronize(void* stream) {
   PBL_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return kOk;

@@ -19,8 +19,18 @@ The reference is single-process; this is the B200-native s
 The per-column sorts never communicate (columns partition naturally); the only reduction is the
 K x K Gram.  The choreography is independent of the compute backend: ``CudaStages`` drives the C ABI
 (the product path); the CPU test-suite plugs a NumPy stand-in to exercise the exchanges on gloo.
+
+Two transports move the transposes:
+
+* **peer copies** (``CudaPeerTransport``, the product path on a box of B200s): every rank maps its peers'
+  column / row buffers with CUDA IPC and the COPY ENGINES write (or, for Y, read) the slices straight
+  over NVLink (``pbl_peer_copy_many``) on a side stream -- no SM is taken from the sorts that run
+  meanwhile, which NCCL's send/recv kernels do (measured: +10 % on every sort they overlap).  A
+  one-element NCCL all-reduce on the same side stream is the cross-rank "round has landed" barrier.
+* **send/recv** (``torch.distributed`` P2P ops; gloo on CPU, NCCL if ``PBL_DIST_EXCHANGE=sendrecv``).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -66,8 +76,17 @@ class CudaStages:
             self.scores_cols = torch.as_tensor(_DevBuf(self.sort_plan.buffer(0)[0], (kc, n_total)), device=dev)
         else:
             self.scores_cols = torch.empty((0, n_total), dtype=torch.float64, device=dev)
-        self.x_cols = torch.empty((kc, n_total), dtype=torch.float64, device=dev)
+        # allocated by the library so that the pointer is the base of a device allocation (CUDA IPC)
+        self._x_ptr = C.c_void_p()
+        _lib.check(self.lib.pbl_device_malloc(C.byref(self._x_ptr), max(kc, 1) * n_total * 8), "pbl_device_malloc")
+        self.x_cols = torch.as_tensor(_DevBuf(self._x_ptr.value, (max(kc, 1), n_total)), device=dev)[:kc]
         self.y_cols = self.x_cols  # X's columns are dead once ranked: reuse for Y's columns
+
+    def exportable(self):
+        """Base device pointers peers may map: name -> pointer (None if this rank has no such buffer)."""
+        return {"x": self._x_ptr.value if self.kc > 0 else None,
+                "scols": self.sort_plan.buffer(0)[0] if self.sort_plan is not None else None,
+                "srows": self.row_plan.buffer(0)[0]}
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -107,6 +126,107 @@ class CudaStages:
         for p in (self.row_plan, self.sort_plan):
             if p is not None:
                 p.close()
+        if self._x_ptr is not None and self._x_ptr.value:
+            self.x_cols = self.y_cols = None
+            self.lib.pbl_device_free(self._x_ptr)
+            self._x_ptr = None
+
+
+class CudaPeerTransport:
+    """Peer copies over NVLink: CUDA IPC mappings of every rank's "x" (X / Y columns), "scols" (scores of
+    the owned columns) and "srows" (scores of the owned rows) buffers, copy engines for the data, a
+    one-element all-reduce as barrier, all on one side stream.  A location is (rank, name, element
+    offset) or (None, tensor, element offset) for the caller's own tensors."""
+
+    def __init__(self, stages, dist):
+        self.torch = torch = stages.torch
+        self.lib = stages.lib
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        mine = {}
+        for name, ptr in stages.exportable().items():
+            if ptr is not None:
+                h = (C.c_ubyte * 64)()
+                _lib.check(self.lib.pbl_ipc_export(C.c_void_p(ptr), h), "pbl_ipc_export")
+                mine[name] = bytes(h)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        self.ptr = {}
+        self._opened = []
+        for name, local in stages.exportable().items():
+            table = []
+            for g in range(self.world):
+                if g == self.rank:
+                    table.append(local)
+                elif name in everyone[g]:
+                    p = C.c_void_p()
+                    h = (C.c_ubyte * 64).from_buffer_copy(everyone[g][name])
+                    _lib.check(self.lib.pbl_ipc_open(h, C.byref(p)), "pbl_ipc_open")
+                    self._opened.append(p.value)
+                    table.append(p.value)
+                else:
+                    table.append(None)
+            self.ptr[name] = table
+        self.side = torch.cuda.Stream()
+        self.token = torch.zeros(1, device="cuda")
+        self.barrier()
+
+    def _addr(self, loc):
+        rank, what, off = loc
+        base = what.data_ptr() if rank is None else self.ptr[what][rank]
+        return base + 8 * off
+
+    def barrier(self):
+        self.dist.all_reduce(self.token)
+
+    def compute_event(self):
+        ev = self.torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def _copies(self, copies):
+        n = len(copies)
+        if n:
+            dst = (C.c_void_p * n)(*[self._addr(c[0]) for c in copies])
+            src = (C.c_void_p * n)(*[self._addr(c[1]) for c in copies])
+            nb = (C.c_uint64 * n)(*[8 * c[2] for c in copies])
+            _lib.check(self.lib.pbl_peer_copy_many(n, dst, src, nb, C.c_void_p(self.side.cuda_stream)),
+                       "pbl_peer_copy_many")
+
+    def push(self, copies, after, barrier=True):
+        """After `after` (a compute-stream event): copy, then (optionally) barrier.  Returns the event that
+        says "every rank's copies of this call have landed"."""
+        torch = self.torch
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(after)
+            self._copies(copies)
+            if barrier:
+                self.barrier()
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev
+
+    def pull(self, copies, after):
+        """After every rank has reached `after`: copy (reads of the peers' buffers)."""
+        torch = self.torch
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(after)
+            self.barrier()
+            self._copies(copies)
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev
+
+    def wait(self, ev):
+        self.torch.cuda.current_stream().wait_event(ev)
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+        for p in self._opened:
+            self.lib.pbl_ipc_close(C.c_void_p(p))
+        self._opened = []
+        self.dist.barrier()  # nobody frees a buffer a peer still has mapped
 
 
 class DistributedImanConover:
@@ -115,7 +235,7 @@ class DistributedImanConover:
     ``X_local`` / ``Y_local`` are (n_local, K) tensors stored column-major (stride (1, n_local)).
     """
 
-    def __init__(self, n_local, k, correlation_matrix, dist, stages=None, device=None):
+    def __init__(self, n_local, k, correlation_matrix, dist, stages=None, device=None, transport=None):
         self.dist = dist
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
@@ -133,6 +253,17 @@ class DistributedImanConover:
             device = torch.cuda.current_device() if device is None else device
             stages = CudaStages(self.n_local, self.n_total, self.k, self.kc, self.P, device)
         self.st = stages
+        if transport is None and isinstance(stages, CudaStages) and self.world > 1 \
+                and os.environ.get("PBL_DIST_EXCHANGE", "peer") == "peer":
+            transport = CudaPeerTransport(stages, dist)
+        self.tp = transport  # None: torch.distributed send/recv rounds
+        self.trace = None  # developer aid (tools/dist_trace.py): list of (label, CUDA event) when enabled
+
+    def _mark(self, label):
+        if self.trace is not None:
+            ev = self.st.torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
 
     # ------------------------------------------------------------------ exchanges
     # A transpose is done in ROUNDS: in round r every rank g exchanges what belongs to its r-th local
@@ -194,36 +325,107 @@ class DistributedImanConover:
         Yc = Y_local.T
         assert Xc.is_contiguous() and Yc.is_contiguous(), "X_local / Y_local must be column-major"
         R = self.rounds
+        if self.tp is not None:
+            return self._run_peer(Xc, Yc, Y_local)
         for _attempt in range(2):
             st.begin()
+            self._mark("begin")
             # 1-3: X rows -> columns, rank + score each column, scores columns -> rows, pipelined
             pending = self._round(0, Xc, st.x_cols, True)
             back = []
             for r in range(R):
                 self._wait(pending)
+                self._mark(f"wait x{r}")
                 pending = self._round(r + 1, Xc, st.x_cols, True) if r + 1 < R else []
                 if r < self.kc:
                     st.rank_scores(r, 1)
+                    self._mark(f"rank_scores {r}")
                 back.append(self._round(r, st.scores_rows, st.scores_cols, False))
             for reqs in back:
                 self._wait(reqs)
+            self._mark("wait scores back")
             st.gram_partial()                                # 4
             dist.all_reduce(st.gram)
             dist.all_reduce(st.colsum)
             st.solve_and_transform()                         # 5
+            self._mark("gram+allreduce+transform")
             # 6-8: correlated scores rows -> columns, rank + gather, Y columns -> rows, pipelined
             pending = self._round(0, st.scores_rows, st.scores_cols, True)
             back = []
             for r in range(R):
                 self._wait(pending)
+                self._mark(f"wait s{r}")
                 pending = self._round(r + 1, st.scores_rows, st.scores_cols, True) if r + 1 < R else []
                 if r < self.kc:
                     st.rank_gather(r, 1)
+                    self._mark(f"rank_gather {r}")
                 back.append(self._round(r, Yc, st.y_cols, False))
             for reqs in back:
                 self._wait(reqs)
+            self._mark("wait y back")
             status = self._agree(st.status())
+            self._mark("status")
             if status != 6:  # PBL_RETRY: some rank switched to the exact 64-bit sort; run again
+                break
+        _raise_for_status(status)
+        return Y_local
+
+    # ------------------------------------------------------------------ the transform, peer copies
+    def _run_peer(self, Xc, Yc, Y_local):
+        """Same pipeline with the peer-copy transport.  Buffer hazards: a rank's buffers are only written by
+        peers (a) after a barrier that follows the owner's last read of them, and every call ends with an
+        all-reduce (the status agreement), so the next call's first pushes find all buffers free."""
+        st, tp, dist = self.st, self.tp, self.dist
+        nl, nt, me = self.n_local, self.n_total, self.rank
+        R = self.rounds
+        blocks = self.blocks
+
+        def x_to_cols(r, src):      # every rank -> owner g: row slice of local column a_g + r
+            return [((g, "x" if src is Xc else "scols", r * nt + me * nl), (None, src, (a + r) * nl), nl)
+                    for g, (a, b) in enumerate(blocks) if r < b - a]
+
+        for _attempt in range(2):
+            st.begin()
+            self._mark("begin")
+            # 1-3: X rows -> columns (push), rank + score each column, scores columns -> rows (push)
+            landed = tp.push(x_to_cols(0, Xc), tp.compute_event())
+            backs = []
+            for r in range(R):
+                tp.wait(landed)
+                self._mark(f"wait x{r}")
+                if r + 1 < R:
+                    landed = tp.push(x_to_cols(r + 1, Xc), tp.compute_event())
+                if r < self.kc:
+                    st.rank_scores(r, 1)
+                    self._mark(f"rank_scores {r}")
+                back = [((g, "srows", (self.c0 + r) * nl), (me, "scols", r * nt + g * nl), nl)
+                        for g in range(self.world)] if r < self.kc else []
+                backs.append(tp.push(back, tp.compute_event(), barrier=(r == R - 1)))
+            tp.wait(backs[-1])  # the side stream is ordered: the last barrier covers every round
+            self._mark("wait scores back")
+            st.gram_partial()                                # 4
+            dist.all_reduce(st.gram)
+            dist.all_reduce(st.colsum)
+            st.solve_and_transform()                         # 5
+            self._mark("gram+allreduce+transform")
+            # 6-8: correlated scores rows -> columns (push), rank + gather, Y columns -> rows (pull)
+            landed = tp.push(x_to_cols(0, st.scores_rows), tp.compute_event())
+            pulls = []
+            for r in range(R):
+                tp.wait(landed)
+                self._mark(f"wait s{r}")
+                if r + 1 < R:
+                    landed = tp.push(x_to_cols(r + 1, st.scores_rows), tp.compute_event())
+                if r < self.kc:
+                    st.rank_gather(r, 1)
+                    self._mark(f"rank_gather {r}")
+                pulls.append(tp.pull([((None, Yc, (a + r) * nl), (g, "x", r * nt + me * nl), nl)
+                                      for g, (a, b) in enumerate(blocks) if r < b - a], tp.compute_event()))
+            tp.wait(pulls[-1])
+            self._mark("wait y back")
+            status = self._agree(st.status())
+            self._mark("status")
+            if status != 6:
                 break
         _raise_for_status(status)
         return Y_local
@@ -239,5 +441,8 @@ class DistributedImanConover:
         return int(t.item())
 
     def close(self):
+        if self.tp is not None:
+            self.tp.close()
+            self.tp = None
         if hasattr(self.st, "close"):
             self.st.close()
