@@ -67,6 +67,7 @@ PBL_API int pbl_stream_synchronize(void* stream);
 PBL_API int pbl_ipc_export(const void* ptr_dev, void* handle64);
 PBL_API int pbl_ipc_open(const void* handle64, void** ptr_dev);
 PBL_API int pbl_ipc_close(void* ptr_dev);
+PBL_API int pbl_peer_copy_streams(int32_t n); /* side streams used by copy_many: 1..8, default 4 */
 PBL_API int pbl_peer_copy_many(int32_t count, void* const* dst_dev, const void* const* src_dev,
                                const uint64_t* bytes, void* stream);
 
@@ -158,6 +159,15 @@ PBL_API int pbl_ic_stage_transform(pbl_ic_plan* plan, void* stream);
 PBL_API int pbl_ic_stage_rank_gather(pbl_ic_plan* plan, double* Y_dev, int64_t row_stride,
                              int64_t col_stride, int32_t col0, int32_t ncols, void* stream);
 PBL_API int pbl_ic_stage_status(pbl_ic_plan* plan, void* stream);
+
+/* Row-chunk hook for a multi-GPU driver: while set (fn != NULL), the scatter by row that ends
+ * rank_scores / rank_gather is enqueued chunk by chunk -- chunk g = output rows [g*chunk_rows,
+ * (g+1)*chunk_rows), in the order first_chunk, first_chunk+1, ... wrapping -- and fn(column, g, user) is
+ * called on the calling thread right after chunk g has been enqueued on the stream, so the driver can
+ * send that row range to its owner while the rest is still being delivered. */
+typedef void (*pbl_chunk_fn)(int32_t column, int32_t chunk, void* user);
+PBL_API int pbl_ic_plan_set_chunk_hook(pbl_ic_plan* plan, int64_t chunk_rows, int32_t first_chunk,
+                                       pbl_chunk_fn fn, void* user);
 
 /* Device pointers to the plan's intermediates (column-major [k][n] unless noted), for parity
  * tests and for collectives: what = 0 scores / correlated scores, 1 sortedX, 2 gram [k][k],

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pbl_ipc_export": (C.c_int, [_vp, _vp]),
     "pbl_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "pbl_ipc_close": (C.c_int, [_vp]),
+    "pbl_peer_copy_streams": (C.c_int, [_i32]),
     "pbl_peer_copy_many": (C.c_int, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp]),
     "pbl_ic_plan_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_vp)]),
     "pbl_ic_plan_create_ex": (C.c_int, [_i64, _i32, _i32, _i32, C.POINTER(_vp)]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "pbl_ic_stage_transform": (C.c_int, [_vp, _vp]),
     "pbl_ic_stage_rank_gather": (C.c_int, [_vp, _pd, _i64, _i64, _i32, _i32, _vp]),
     "pbl_ic_stage_status": (C.c_int, [_vp, _vp]),
+    "pbl_ic_plan_set_chunk_hook": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "pbl_ic_plan_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_u64)]),
     "pbl_uniform_f64": (C.c_int, [_u64, _u64, _i64, _i32, _pd, _i64, _i64, _vp]),
     "pbl_sobol_direction_numbers": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
@@ -73,6 +75,9 @@ SIGNATURES = {
     "pbl_graph_eval_f64": (C.c_int, [_vp, _i32, _i32, _i64, _u64, _vp, _i32, _vp, _i32, C.POINTER(_i32), _vp]),
     "pbl_ppf_f64": (C.c_int, [_i32, _pd, _i64, C.c_double, C.c_double, C.c_double, _pd, _vp]),
 }
+
+
+CHUNK_FN = C.CFUNCTYPE(None, _i32, _i32, _vp)  # pbl_chunk_fn
 
 
 class GraphInstr(C.Structure):

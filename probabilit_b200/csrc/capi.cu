@@ -95,7 +95,8 @@ int pbl_ipc_close(void* ptr_dev) {
 }
 
 namespace {
-constexpr int kCopyStreams = 4;
+constexpr int kCopyStreams = 8;  // pool size; g_copy_streams of them are used
+int g_copy_streams = 4;
 struct CopyPool {
   bool ready = false;
   cudaStream_t s[kCopyStreams];
@@ -103,6 +104,12 @@ struct CopyPool {
 };
 CopyPool g_copy_pool[64];
 }  // namespace
+
+int pbl_peer_copy_streams(int32_t n) {
+  if (n < 1 || n > kCopyStreams) return kBadShape;
+  g_copy_streams = n;
+  return kOk;
+}
 
 // `count` device-to-device copies (local or peer-mapped pointers, any mix), spread over a small
 // pool of side streams so that several copy engines / NVLink ports work at once; ordered after
@@ -122,12 +129,13 @@ int pbl_peer_copy_many(int32_t count, void* const* dst, const void* const* src, 
     cp.ready = true;
   }
   cudaStream_t main = (cudaStream_t)stream;
-  const int used = count < kCopyStreams ? count : kCopyStreams;
+  const int width = g_copy_streams;
+  const int used = count < width ? count : width;
   PBL_CUDA_CHECK(cudaEventRecord(cp.fork, main));
   for (int i = 0; i < used; ++i) PBL_CUDA_CHECK(cudaStreamWaitEvent(cp.s[i], cp.fork, 0));
   for (int i = 0; i < count; ++i)
     if (bytes[i])
-      PBL_CUDA_CHECK(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, cp.s[i % kCopyStreams]));
+      PBL_CUDA_CHECK(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, cp.s[i % width]));
   for (int i = 0; i < used; ++i) {
     PBL_CUDA_CHECK(cudaEventRecord(cp.join[i], cp.s[i]));
     PBL_CUDA_CHECK(cudaStreamWaitEvent(main, cp.join[i], 0));
@@ -280,6 +288,17 @@ int pbl_ic_stage_rank_gather(pbl_ic_plan* plan, double* Y, int64_t rs, int64_t c
 int pbl_ic_stage_status(pbl_ic_plan* plan, void* stream) {
   if (!plan) return kBadShape;
   return pbl::ic_read_status(plan->impl, (cudaStream_t)stream);
+}
+
+int pbl_ic_plan_set_chunk_hook(pbl_ic_plan* plan, int64_t chunk_rows, int32_t first_chunk, pbl_chunk_fn fn,
+                               void* user) {
+  if (!plan) return kBadShape;
+  pbl::IcPlan* p = plan->impl;
+  p->chunk_rows = fn ? chunk_rows : 0;
+  p->chunk_first = first_chunk;
+  p->chunk_fn = fn;
+  p->chunk_user = user;
+  return kOk;
 }
 
 int pbl_ic_plan_buffer(pbl_ic_plan* plan, int32_t what, void** ptr, uint64_t* bytes) {

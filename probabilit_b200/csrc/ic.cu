@@ -1145,6 +1145,31 @@ static int post_sort_attr() {
   return kOk;
 }
 
+// The scatter by row, in one launch or (row-chunk hook set) chunk by chunk with the hook called after each.
+static int scatter_rows_hooked(IcPlan* p, int c, int nb, int shift, double* out, int64_t row_stride,
+                               int64_t col_stride, cudaStream_t stream) {
+  const uint32_t n = (uint32_t)p->n;
+  if (!p->chunk_fn || p->chunk_rows <= 0) return scatter_rows(n, nb, sort_view(p), out, row_stride, col_stride, stream);
+  const int nchunks = (int)((p->n + p->chunk_rows - 1) / p->chunk_rows);
+  if (shift >= 32) {  // short columns: the pairs are not grouped by row window
+    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), out, row_stride, col_stride, stream));
+    for (int i = 0; i < nchunks; ++i)
+      for (int j = 0; j < nb; ++j) p->chunk_fn(c + j, (p->chunk_first + i) % nchunks, p->chunk_user);
+    return kOk;
+  }
+  const uint64_t w = 1ull << shift;
+  for (int i = 0; i < nchunks; ++i) {
+    const int g = (p->chunk_first + i) % nchunks;
+    // whole windows covering the chunk's rows (a window shared with the neighbouring chunk is delivered
+    // twice, with identical values)
+    const uint64_t lo = (uint64_t)g * p->chunk_rows / w * w;
+    const uint64_t hi = std::min<uint64_t>(n, (std::min<uint64_t>(n, (uint64_t)(g + 1) * p->chunk_rows) + w - 1) / w * w);
+    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), out, row_stride, col_stride, stream, (uint32_t)lo, (uint32_t)hi));
+    for (int j = 0; j < nb; ++j) p->chunk_fn(c + j, g, p->chunk_user);
+  }
+  return kOk;
+}
+
 int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t col_stride,
                          int col0, int ncols, cudaStream_t stream, bool ranks_only) {
   if (p->rows_only) {
@@ -1178,7 +1203,7 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
           p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
           ntiles);
     PBL_LAUNCH_CHECK();
-    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), p->scores + (size_t)c * n, 1, (int64_t)n, stream));
+    PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, p->scores + (size_t)c * n, 1, (int64_t)n, stream));
   }
   return kOk;
 }
@@ -1261,8 +1286,8 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
         p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
         ntiles);
     PBL_LAUNCH_CHECK();
-    PBL_RETURN_IF(scatter_rows(n, nb, sort_view(p), Y + (int64_t)c * col_stride, row_stride, col_stride,
-                               stream));
+    PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, Y + (int64_t)c * col_stride, row_stride, col_stride,
+                                      stream));
   }
   return kOk;
 }

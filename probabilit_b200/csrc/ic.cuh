@@ -36,6 +36,13 @@ struct IcPlan {
   std::vector<cudaEvent_t> events;
   void* permcorr = nullptr;    // PermutationCorrelator state (permcorr.cu), lazy
   uint32_t* flags = nullptr;   // [8], see SortFlag in sort.cuh
+  // row-chunk hook (multi-GPU driver): the scatter by row that ends rank_scores / rank_gather is issued
+  // chunk by chunk (chunk g = output rows [g * chunk_rows, (g+1) * chunk_rows), starting with chunk_first
+  // and wrapping) and chunk_fn(column, g, user) is called on the host right after chunk g is enqueued
+  int64_t chunk_rows = 0;
+  int chunk_first = 0;
+  void (*chunk_fn)(int32_t, int32_t, void*) = nullptr;
+  void* chunk_user = nullptr;
   size_t bytes = 0;            // device bytes held by the plan
 };
 

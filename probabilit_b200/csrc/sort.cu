@@ -692,7 +692,8 @@ __global__ void __launch_bounds__(256)
 scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restrict__ keysB,
                     const uint32_t* __restrict__ valsA, const uint32_t* __restrict__ valsB,
                     const PassPlan* __restrict__ plan, uint32_t n, int partitioned,
-                    double* __restrict__ out, int64_t out_row_stride, int64_t out_col_stride) {
+                    double* __restrict__ out, int64_t out_row_stride, int64_t out_col_stride,
+                    uint32_t pos_begin, uint32_t pos_end) {
   const int col = blockIdx.y;
   const int fb = plan[col].final_buf;
   const int ob = (fb == 1) ? 2 : 1;
@@ -702,13 +703,13 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
   const uint64_t* vals = (b == 1 ? keysA : keysB) + (size_t)col * n;
   double* outc = out + (int64_t)col * out_col_stride;
   constexpr int U = 8;
-  const uint32_t base = blockIdx.x * (256u * U) + threadIdx.x;
+  const uint32_t base = pos_begin + blockIdx.x * (256u * U) + threadIdx.x;  // pos_end <= n < 2^30: no overflow
   uint32_t r[U];
   uint64_t v[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     uint32_t i = base + u * 256u;
-    if (i < n) {
+    if (i < pos_end) {
       r[u] = ld_stream_u32(rows + i);
       v[u] = ld_stream_u64(vals + i);
     }
@@ -716,7 +717,7 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     uint32_t i = base + u * 256u;
-    if (i < n) outc[(int64_t)r[u] * out_row_stride] = __longlong_as_double((long long)v[u]);
+    if (i < pos_end) outc[(int64_t)r[u] * out_row_stride] = __longlong_as_double((long long)v[u]);
   }
 }
 
@@ -949,11 +950,12 @@ int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_s
 }
 
 int scatter_rows(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
-                 int64_t col_stride, cudaStream_t stream) {
-  if (n == 0 || ncols <= 0) return kOk;
-  dim3 grid((unsigned)(((size_t)n + 2047) / 2048), (unsigned)ncols);
+                 int64_t col_stride, cudaStream_t stream, uint32_t pos_begin, uint32_t pos_end) {
+  pos_end = std::min(pos_end, n);
+  if (n == 0 || ncols <= 0 || pos_begin >= pos_end) return kOk;
+  dim3 grid((unsigned)(((size_t)(pos_end - pos_begin) + 2047) / 2048), (unsigned)ncols);
   scatter_rows_kernel<<<grid, 256, 0, stream>>>(buf.keysA, buf.keysB, buf.valsA, buf.valsB, buf.plan,
-                                               n, 0, out, row_stride, col_stride);
+                                               n, 0, out, row_stride, col_stride, pos_begin, pos_end);
   PBL_LAUNCH_CHECK();
   return kOk;
 }

@@ -180,7 +180,10 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
 int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_stride, bool use_lookback,
                     int consumer_tile, int* shift_out, int* ntiles_out, uint32_t** tile_counter_out,
                     cudaStream_t stream);
+// [pos_begin, pos_end): the staged positions to deliver.  With grouped pairs (shift < 32) the pairs of
+// rows [a << shift, b << shift) are exactly the positions [a << shift, b << shift), so a caller can
+// deliver the output row range by row range (the multi-GPU driver sends each range off as it completes).
 int scatter_rows(uint32_t n, int ncols, const SortBuffers& buf, double* out, int64_t row_stride,
-                 int64_t col_stride, cudaStream_t stream);
+                 int64_t col_stride, cudaStream_t stream, uint32_t pos_begin = 0, uint32_t pos_end = 0xFFFFFFFFu);
 
 }  // namespace pbl

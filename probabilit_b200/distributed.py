@@ -96,11 +96,39 @@ class CudaStages:
             if p is not None:
                 _lib.check(self.lib.pbl_ic_stage_begin(p.handle, self._stream()))
 
-    def rank_scores(self, ci=0, nci=None):  # x_cols -> scores_cols (+ sortedX kept inside the sort plan)
+    class _ChunkHook:
+        """Scope of the row-chunk hook (pbl_ic_plan_set_chunk_hook): on_chunk(g) is called as soon as the
+        rows [g * n_local, (g+1) * n_local) of the stage's output have been enqueued, rank `first` first."""
+
+        def __init__(self, stages, on_chunk, first):
+            self.st, self.on_chunk, self.first, self.error = stages, on_chunk, first, None
+
+        def __enter__(self):
+            if self.on_chunk is not None:
+                def trampoline(_col, g, _user):
+                    try:
+                        self.on_chunk(int(g))
+                    except BaseException as e:  # must not propagate through the C frame
+                        self.error = self.error or e
+                self.cb = _lib.CHUNK_FN(trampoline)
+                _lib.check(self.st.lib.pbl_ic_plan_set_chunk_hook(
+                    self.st.sort_plan.handle, self.st.n_local, self.first, self.cb, None))
+            return self
+
+        def __exit__(self, *exc):
+            if self.on_chunk is not None:
+                self.st.lib.pbl_ic_plan_set_chunk_hook(self.st.sort_plan.handle, 0, 0, None, None)
+                if self.error is not None and exc[0] is None:
+                    raise self.error
+            return False
+
+    def rank_scores(self, ci=0, nci=None, on_chunk=None, first_chunk=0):
+        """x_cols -> scores_cols (+ sortedX kept inside the sort plan)"""
         nci = self.kc - ci if nci is None else nci
         if nci > 0:
-            _lib.check(self.lib.pbl_ic_stage_rank_scores(
-                self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
+            with self._ChunkHook(self, on_chunk, first_chunk):
+                _lib.check(self.lib.pbl_ic_stage_rank_scores(
+                    self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
 
     def gram_partial(self):  # scores_rows -> gram, colsum (local partial sums)
         _lib.check(self.lib.pbl_ic_stage_gram(self.row_plan.handle, self._stream()))
@@ -109,11 +137,13 @@ class CudaStages:
         _lib.check(self.lib.pbl_ic_stage_solve(self.row_plan.handle, self.n_total, self._stream()))
         _lib.check(self.lib.pbl_ic_stage_transform(self.row_plan.handle, self._stream()))
 
-    def rank_gather(self, ci=0, nci=None):  # scores_cols (correlated) -> y_cols
+    def rank_gather(self, ci=0, nci=None, on_chunk=None, first_chunk=0):
+        """scores_cols (correlated) -> y_cols"""
         nci = self.kc - ci if nci is None else nci
         if nci > 0:
-            _lib.check(self.lib.pbl_ic_stage_rank_gather(
-                self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
+            with self._ChunkHook(self, on_chunk, first_chunk):
+                _lib.check(self.lib.pbl_ic_stage_rank_gather(
+                    self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
 
     def status(self):
         st = 0
@@ -185,6 +215,15 @@ class CudaPeerTransport:
         return ev
 
     def _copies(self, copies):
+        # local <- local moves go through a copy KERNEL on the side stream (a copy engine moves local HBM
+        # at well under 1 TB/s, a kernel at 2.5 TB/s); everything that crosses NVLink uses the engines
+        def is_local(c):
+            return c[0][0] in (None, self.rank) and c[1][0] in (None, self.rank)
+
+        for dst, src, cnt in (c for c in copies if is_local(c)):
+            d = self.torch.as_tensor(_DevBuf(self._addr(dst), (cnt,)), device="cuda")
+            d.copy_(self.torch.as_tensor(_DevBuf(self._addr(src), (cnt,)), device="cuda"))
+        copies = [c for c in copies if not is_local(c)]
         n = len(copies)
         if n:
             dst = (C.c_void_p * n)(*[self._addr(c[0]) for c in copies])
@@ -380,28 +419,33 @@ class DistributedImanConover:
         R = self.rounds
         blocks = self.blocks
 
+        # peers in staggered order (me+1, me+2, ..., me): at any moment every rank writes to (reads from)
+        # a different peer, so no receiver's NVLink ingress is shared by several senders
+        ring = [(me + 1 + i) % self.world for i in range(self.world)]
+
         def x_to_cols(r, src):      # every rank -> owner g: row slice of local column a_g + r
-            return [((g, "x" if src is Xc else "scols", r * nt + me * nl), (None, src, (a + r) * nl), nl)
-                    for g, (a, b) in enumerate(blocks) if r < b - a]
+            return [((g, "x" if src is Xc else "scols", r * nt + me * nl), (None, src, (blocks[g][0] + r) * nl), nl)
+                    for g in ring if r < blocks[g][1] - blocks[g][0]]
 
         for _attempt in range(2):
             st.begin()
             self._mark("begin")
             # 1-3: X rows -> columns (push), rank + score each column, scores columns -> rows (push)
+            # (the way back is sent row range by row range while the scatter that ends the stage is still
+            # delivering the rest: chunk g = the rows of rank g, the ring successor first)
             landed = tp.push(x_to_cols(0, Xc), tp.compute_event())
-            backs = []
             for r in range(R):
                 tp.wait(landed)
                 self._mark(f"wait x{r}")
                 if r + 1 < R:
                     landed = tp.push(x_to_cols(r + 1, Xc), tp.compute_event())
                 if r < self.kc:
-                    st.rank_scores(r, 1)
+                    st.rank_scores(r, 1, first_chunk=ring[0], on_chunk=lambda g, r=r: tp.push(
+                        [((g, "srows", (self.c0 + r) * nl), (me, "scols", r * nt + g * nl), nl)],
+                        tp.compute_event(), barrier=False))
                     self._mark(f"rank_scores {r}")
-                back = [((g, "srows", (self.c0 + r) * nl), (me, "scols", r * nt + g * nl), nl)
-                        for g in range(self.world)] if r < self.kc else []
-                backs.append(tp.push(back, tp.compute_event(), barrier=(r == R - 1)))
-            tp.wait(backs[-1])  # the side stream is ordered: the last barrier covers every round
+            # the side stream is ordered: one barrier after the last chunk covers every round
+            tp.wait(tp.push([], tp.compute_event(), barrier=True))
             self._mark("wait scores back")
             st.gram_partial()                                # 4
             dist.all_reduce(st.gram)
@@ -416,11 +460,16 @@ class DistributedImanConover:
                 self._mark(f"wait s{r}")
                 if r + 1 < R:
                     landed = tp.push(x_to_cols(r + 1, st.scores_rows), tp.compute_event())
+                # Y travels like the scores did: pushed, chunk by chunk, into the owners' row buffer (whose
+                # column a_g + r is dead: it was sent off in round r of step 6), then copied locally into Y
+                # (NVLink reads are slower than writes: 350-400 vs 530 GB/s per GPU on this box)
                 if r < self.kc:
-                    st.rank_gather(r, 1)
+                    st.rank_gather(r, 1, first_chunk=ring[0], on_chunk=lambda g, r=r: tp.push(
+                        [((g, "srows", (self.c0 + r) * nl), (me, "x", r * nt + g * nl), nl)],
+                        tp.compute_event(), barrier=False))
                     self._mark(f"rank_gather {r}")
-                pulls.append(tp.pull([((None, Yc, (a + r) * nl), (g, "x", r * nt + me * nl), nl)
-                                      for g, (a, b) in enumerate(blocks) if r < b - a], tp.compute_event()))
+                pulls.append(tp.pull([((None, Yc, (blocks[g][0] + r) * nl), (me, "srows", (blocks[g][0] + r) * nl), nl)
+                                      for g in ring if r < blocks[g][1] - blocks[g][0]], tp.compute_event()))
             tp.wait(pulls[-1])
             self._mark("wait y back")
             status = self._agree(st.status())

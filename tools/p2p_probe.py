@@ -70,12 +70,52 @@ def main():
         e1.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms = timed(push_round)
+    for width in (1, 2, 4, 8):
+        _lib.check(lib.pbl_peer_copy_streams(width))
+        ms = timed(push_round)
+        out[f"ce{width}_round_ms"] = ms
+        out[f"ce{width}_out_GBps_per_gpu"] = (world - 1) * nl * 8 / ms / 1e6
     mine = torch.as_tensor(_Buf(buf.value, (world, nl)), device="cuda")
-    ok = all(bool((mine[g] == g + 1).all()) for g in range(world))
-    out["ce_round_ms"] = ms
-    out["ce_out_GBps_per_gpu"] = (world - 1) * nl * 8 / ms / 1e6
-    out["ce_data_ok"] = ok
+    out["ce_data_ok"] = all(bool((mine[g] == g + 1).all()) for g in range(world))
+
+    def pull_round():  # the Y direction: read the peers' slices
+        order = [(rank + 1 + i) % world for i in range(world)]
+        n = len(order)
+        srcs = (C.c_void_p * n)(*[peers[g] + rank * nl * 8 for g in order])
+        dst = (C.c_void_p * n)(*[recv0.data_ptr() + g * nl * 8 for g in order])
+        nb = (C.c_uint64 * n)(*[nl * 8] * n)
+        dist.all_reduce(token)
+        _lib.check(lib.pbl_peer_copy_many(n, dst, srcs, nb, sp))
+
+    recv0 = torch.empty((world, nl), dtype=torch.float64, device="cuda")
+    for width in (2, 4, 8):
+        _lib.check(lib.pbl_peer_copy_streams(width))
+        ms = timed(pull_round)
+        out[f"pull{width}_round_ms"] = ms
+        out[f"pull{width}_in_GBps_per_gpu"] = (world - 1) * nl * 8 / ms / 1e6
+    del recv0
+
+    # SM-driven peer stores (an elementwise kernel writing through the IPC mapping), for comparison
+    views = [torch.as_tensor(_Buf(peers[g] + rank * nl * 8, (nl,)), device="cuda") for g in range(world)]
+    side = [torch.cuda.Stream() for _ in range(4)]
+
+    def kernel_round():
+        ev = torch.cuda.Event()
+        ev.record()
+        for i in range(world):
+            g = (rank + 1 + i) % world
+            with torch.cuda.stream(side[i % 4]):
+                side[i % 4].wait_event(ev)
+                views[g].copy_(src)
+        for st_ in side:
+            e = torch.cuda.Event()
+            e.record(st_)
+            torch.cuda.current_stream().wait_event(e)
+        dist.all_reduce(token)
+
+    ms = timed(kernel_round)
+    out["sm_store_round_ms"] = ms
+    out["sm_store_out_GBps_per_gpu"] = (world - 1) * nl * 8 / ms / 1e6
 
     recv = torch.empty((world, nl), dtype=torch.float64, device="cuda")
 
@@ -104,7 +144,7 @@ def main():
     res = [None] * world
     dist.all_gather_object(res, out)
     if rank == 0:
-        print(json.dumps(res, indent=1))
+        print(json.dumps(res[0], indent=1))
     dist.destroy_process_group()
 
 
