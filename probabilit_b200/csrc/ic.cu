@@ -37,8 +37,10 @@ constexpr int kPostItems = 4;
 constexpr int kPostTile = kPostBlock * kPostItems;
 constexpr int kHalo = 64;                      // window values may repeat in runs of < kHalo keys
 constexpr int kWin = kPostTile + 2 * kHalo;
+constexpr int kMaxRun = 32;                    // ... and are re-ordered here when shorter than this
 constexpr size_t kPostSmem = (size_t)kWin * 8 * 2 + (size_t)kWin * 4 * 2 + (size_t)kPostTile * 4 * 2 + 128 +
-                             3 * kRadix * 4 + 16;
+                             3 * kRadix * 4 + 16 + (kWin / 32) * 4 + sizeof(KeyMap);
+static_assert(kWin % 32 == 0 && kHalo >= 2 * kMaxRun - 1, "run masks are per 32 slots; halo covers two runs");
 
 __device__ __forceinline__ uint32_t block_excl_prefix_max(uint32_t v, uint32_t* s_w) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256) vdw_table_kernel(uint32_t n, double* __re
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kPostBlock)
+__global__ void __launch_bounds__(kPostBlock, 3)
 post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB,
                  const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
                  int window_bits, uint32_t n, double* __restrict__ sortedX,
@@ -114,7 +116,9 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* s_cnt = s_lohi + 4;                              // [kRadix] elements per destination window
   uint32_t* s_bstart = s_cnt + kRadix;                       // [kRadix]
   uint32_t* s_goff = s_bstart + kRadix;                      // [kRadix]
-  uint32_t* s_ticket = s_goff + kRadix;                      // [1]
+  uint32_t* s_ticket = s_goff + kRadix;                      // [1] (+3 pad)
+  uint32_t* s_mask = s_ticket + 4;                           // [kWin / 32] "same window as the slot to the left"
+  KeyMap* s_map = reinterpret_cast<KeyMap*>(s_mask + kWin / 32);  // 8-byte aligned: all sizes above are
   // staging of the partitioned (value, row) pairs: the raw window copies are dead by then
   double* s_pval = reinterpret_cast<double*>(s_raw);         // [kPostTile]
   uint32_t* s_prow = s_rawv;                                 // [kPostTile]
@@ -125,19 +129,18 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   // tiles take tickets so that the look-back between tiles can never wait on a tile that has not
   // started (blockIdx order is not a scheduling guarantee)
   uint32_t tile = blockIdx.x;
-  if (partition) {
-    if (tid == 0) *s_ticket = atomicAdd(&tile_counter[col], 1u);
-    if (tid < kRadix) s_cnt[tid] = 0;
-    __syncthreads();
-    tile = *s_ticket;
-  }
+  if (partition && tid == 0) *s_ticket = atomicAdd(&tile_counter[col], 1u);
+  if (partition && tid < kRadix) s_cnt[tid] = 0;
+  if (tid == 32) *s_map = load_key_map(kminmax, col, window_bits);  // once per block, not per thread
+  __syncthreads();
+  if (partition) tile = *s_ticket;
+  const KeyMap map = *s_map;
   const int fb = plan[col].final_buf;
   const uint64_t* keys = (fb == 1 ? keysA : keysB) + (size_t)col * n;
   const uint32_t* rows_in = (fb == 1 ? valsA : valsB) + (size_t)col * n;
   double* stage = reinterpret_cast<double*>((fb == 1 ? keysB : keysA) + (size_t)col * n);
   uint32_t* rows_out = (fb == 1 ? valsB : valsA) + (size_t)col * n;
   double* sx = sortedX + (size_t)col * n;
-  const KeyMap map = load_key_map(kminmax, col, window_bits);
   const uint32_t tile_start = tile * (uint32_t)kPostTile;
   const uint32_t nvalid = min((uint32_t)kPostTile, n - tile_start);
   const int64_t wbase = (int64_t)tile_start - kHalo;  // global index of window slot 0
@@ -167,62 +170,63 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   __syncthreads();
 
   // ---- (1) complete the order inside runs of equal window values ----
+  // (1a) one bit per slot: "same window value as the slot to its left" (ballot words in shared memory)
   const int lo_i = (int)max((int64_t)0, -wbase);                  // first slot inside the column
   const int hi_i = (int)min((int64_t)kWin, (int64_t)n - wbase);   // one past the last such slot
-  int retry = 0;
+  for (int i = tid; i < kWin; i += kPostBlock) {  // kWin and the tail of the loop are whole warps
+    const bool sl = i > lo_i && i < hi_i && same_window(s_raw[i], s_raw[i - 1], map);
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, sl);
+    if ((tid & 31) == 0) s_mask[i >> 5] = m;
+  }
+  __syncthreads();
+  // (1b) a slot's run is the stretch of set bits around it: its extent comes from bit scans, and only
+  //      members of a run (a fifth of the keys at 0.2 keys per window value) walk it.  Runs of up to
+  //      kMaxRun keys are re-ordered by their full keys (equal keys keep their order); every member sees
+  //      the whole run (kHalo >= 2 kMaxRun - 1 slots on either side of the tile), so all reach the same
+  //      verdict.  A longer run is left as it is -- fine if it is pure (a tie run) -- and any adjacent
+  //      pair of DIFFERENT keys inside it raises kFlagWindowRetry in the tile that owns either key.
+  int retry = 0, tie = 0;
   for (int i = tid; i < kWin; i += kPostBlock) {
     if (i < lo_i || i >= hi_i) continue;
     const uint64_t my = s_raw[i];
     int dst = i;
-    const bool sl = i > lo_i && same_window(my, s_raw[i - 1], map);
-    const bool sr = i + 1 < hi_i && same_window(my, s_raw[i + 1], map);
-    if (sl || sr || (i == 0 && lo_i == 0 && wbase > 0) || (i == kWin - 1 && wbase + kWin < (int64_t)n)) {
-      uint32_t cnt = 0;
-      int L = 0, R = 0;
-      bool diff = false, open = false;
-      for (int j = i - 1;; --j) {
-        if (j < lo_i) { open = (j < 0 && wbase + j >= 0); break; }  // unseen element left of the window?
-        const uint64_t kj = s_raw[j];
-        if (!same_window(kj, my, map)) break;
-        if (L == kHalo) { open = true; break; }
-        cnt += (kj <= my) ? 1u : 0u;                                // equal keys keep their order
-        diff |= (kj != my);
-        ++L;
-      }
-      for (int j = i + 1;; ++j) {
-        if (j >= hi_i) { open |= (j >= kWin && wbase + j < (int64_t)n); break; }
-        const uint64_t kj = s_raw[j];
-        if (!same_window(kj, my, map)) break;
-        if (R == kHalo) { open = true; break; }
-        cnt += (kj < my) ? 1u : 0u;
-        diff |= (kj != my);
-        ++R;
-      }
-      if (L + R + 1 > kHalo - 1) open = true;  // every member of the run must reach the same verdict
-      if (diff) {
-        if (!open) {
-          dst = i - L + (int)cnt;
-        } else if (i + R >= kHalo - 1 && i - L <= kHalo + (int)nvalid) {
-          retry = 1;  // cannot be completed here and it matters for this tile's output
+    const int c = i >> 5, l = i & 31;
+    const uint32_t cur = s_mask[c];
+    const uint32_t prev = c > 0 ? s_mask[c - 1] : 0u;
+    const uint32_t next = c + 1 < kWin / 32 ? s_mask[c + 1] : 0u;
+    const uint64_t left = (((uint64_t)cur << 32) | prev) << (31 - l);      // bit 63 = this slot's flag
+    const uint64_t right = (((uint64_t)next << 32) | cur) >> (l + 1);      // bit 0 = flag of slot i + 1
+    if ((left >> 63) | (right & 1ull)) {
+      const int L = __clzll((long long)~left);                            // set flags at i, i-1, ...
+      const int R = (~right) ? __ffsll((long long)~right) - 1 : 64;        // set flags at i+1, i+2, ...
+      if (L + R + 1 <= kMaxRun) {
+        uint32_t cnt = 0;
+        for (int j = i - L; j <= i + R; ++j) {
+          const uint64_t kj = s_raw[j];
+          cnt += (kj < my || (kj == my && j < i)) ? 1u : 0u;
+          tie |= (kj == my && j != i) ? 1 : 0;
         }
+        dst = i - L + (int)cnt;
+      } else if (L > 0) {
+        const bool differs = s_raw[i - 1] != my;
+        tie |= differs ? 0 : 1;
+        if (differs && i >= kHalo && i - 1 < kHalo + (int)nvalid) retry = 1;
       }
     }
     s_key[dst] = my;
     s_row[dst] = s_rawv[i];
   }
   if (retry) flags[kFlagWindowRetry] = 1u;
-  __syncthreads();
 
   // ---- (2) tie runs.  teq(q): tile position q holds the same value as position q-1
   //      (q = 0 .. nvalid; positions outside the column never tie).  Keys are canonical
-  //      (-0.0 folded onto +0.0), so key equality is value equality. ----
+  //      (-0.0 folded onto +0.0), so key equality is value equality.  Equal keys share a window value,
+  //      so step (1) has seen every tie (possibly one that lies in the halo only: harmless). ----
   auto teq = [&](uint32_t q) -> bool {
     const int64_t g = (int64_t)tile_start + q;  // global index of position q
     if (g <= 0 || g >= (int64_t)n) return false;
     return s_key[kHalo + q] == s_key[kHalo + q - 1];
   };
-  int tie = 0;
-  for (uint32_t q = tid; q <= nvalid; q += kPostBlock) tie |= teq(q) ? 1 : 0;
   tie = __syncthreads_or(tie);
 
   if (tie) {
