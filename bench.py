@@ -293,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
     value = float(n) * d * world * args.steps / (ms * 1e-3)
 
     # parity guard inside the bench: Y is a per-column permutation of X (column 0 untouched)
-    if not torch.equal(X[:, 0], Y[:, 0]) and world == 1:
+    if not torch.equal(X[:, 0], Y[:, 0]):
         raise RuntimeError("bench: column 0 changed -- the transform is broken")
 
     # ---- e2e through the public API with host (pinned) buffers ----
@@ -327,11 +327,47 @@ def run_ours(args, rank, world, local_rank):
         lib.pbl_host_free_pinned(hx)
         lib.pbl_host_free_pinned(hy)
 
+    if world > 1 and args.e2e_steps > 0:
+        # every rank's row shard starts and ends in pinned HOST memory: H2D of the shard, the multi-GPU call,
+        # D2H of the result, all inside the timed region (wall clock, max over ranks)
+        nbytes = n * d * 8
+        hx, hy = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hx), nbytes))
+        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hy), nbytes))
+        _lib.check(lib.pbl_memcpy_d2h(hx, C.c_void_p(X.data_ptr()), nbytes, sp))
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            _lib.check(lib.pbl_memcpy_h2d(C.c_void_p(X.data_ptr()), hx, nbytes, sp))
+            runner.run(X, Y)
+            _lib.check(lib.pbl_memcpy_d2h(hy, C.c_void_p(Y.data_ptr()), nbytes, sp))
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": float(n) * d * world * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "probabilit_b200.distributed.DistributedImanConover.run on row shards copied from / to "
+                      "pinned host memory (one PCIe link per GPU, copies not overlapped with the transform)"}
+        lib.pbl_host_free_pinned(hx)
+        lib.pbl_host_free_pinned(hy)
+
     graph = None
     if world == 1 and args.graph_rows > 0:
         graph = time_graph(args.graph_rows, lib)
 
+    if world > 1:
+        runner.close()  # collective: unmaps the peers' buffers before anybody frees them
     if rank != 0:
+        dist.destroy_process_group()
         return
     peak, peak_src = hbm_peak()
     pass_gbs = PASS_BYTES_PER_KEY * nkeys.value / (pms.value * 1e-3) / 1e9 if pms.value > 0 else None
@@ -364,7 +400,9 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"Iman-Conover fp64 N={n} rows per GPU, d={d}, mixed norm/triang/gamma "
                                "marginals (BASELINE.json configs[2]), pseudo-random uniforms",
                    "rows_per_gpu": n, "d": d, "l2": "inputs (12.8 GB) far exceed the 126 MB L2",
-                   "col_batch": args.col_batch},
+                   "col_batch": args.col_batch,
+                   **({"transport": "row <-> column transposes by copy engines over CUDA-IPC peer mappings "
+                                    "(NVLink), NCCL for the Gram all-reduce and the barriers"} if world > 1 else {})},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "graph": graph,
     }

@@ -709,9 +709,9 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     uint32_t i = base + u * 256u;
-    if (i < pos_end) {
-      r[u] = ld_stream_u32(rows + i);
-      v[u] = ld_stream_u64(vals + i);
+    if (i < pos_end) {  // evict-first: the pairs stream through L2 once, the output lines must stay
+      r[u] = __ldcs(rows + i);
+      v[u] = __ldcs((const unsigned long long*)vals + i);
     }
   }
 #pragma unroll

@@ -18,14 +18,16 @@ from probabilit_b200.distributed import DistributedImanConover, column_blocks
 class NumpyStages:
     """Test stand-in for CudaStages (same attributes / methods), NumPy on CPU tensors."""
 
-    def __init__(self, n_local, n_total, k, kc, P):
+    def __init__(self, n_local, n_total, k, kc, P, buffers=None):
         self.torch = torch
         self.n_local, self.n_total, self.k, self.kc, self.P = n_local, n_total, k, kc, P
         f64 = torch.float64
-        self.x_cols = torch.zeros((kc, n_total), dtype=f64)
+        if buffers is None:
+            buffers = {"x": np.zeros((kc, n_total)), "scols": np.zeros((kc, n_total)), "srows": np.zeros((k, n_local))}
+        self.x_cols = torch.from_numpy(buffers["x"])
         self.y_cols = self.x_cols
-        self.scores_cols = torch.zeros((kc, n_total), dtype=f64)
-        self.scores_rows = torch.zeros((k, n_local), dtype=f64)
+        self.scores_cols = torch.from_numpy(buffers["scols"])
+        self.scores_rows = torch.from_numpy(buffers["srows"])
         self.gram = torch.zeros(k * k, dtype=f64)
         self.colsum = torch.zeros(k, dtype=f64)
         self.sortedX = None
@@ -34,7 +36,13 @@ class NumpyStages:
     def begin(self):
         self._status = 0
 
-    def rank_scores(self, ci=0, nci=None):
+    def _chunks(self, on_chunk, first_chunk):
+        if on_chunk is not None:  # the row-chunk hook of the CUDA stages: every chunk once, first_chunk first
+            world = self.n_total // self.n_local
+            for i in range(world):
+                on_chunk((first_chunk + i) % world)
+
+    def rank_scores(self, ci=0, nci=None, on_chunk=None, first_chunk=0):
         from scipy.special import ndtri
         nci = self.kc - ci if nci is None else nci
         x = self.x_cols.numpy()
@@ -44,6 +52,8 @@ class NumpyStages:
             self.sortedX[c] = np.sort(x[c])
             r, _ = oic.average_ranks(x[c])
             self.scores_cols[c] = torch.from_numpy(ndtri(r / (self.n_total + 1)))
+        if nci > 0:
+            self._chunks(on_chunk, first_chunk)
 
     def gram_partial(self):
         s = self.scores_rows.numpy()
@@ -65,14 +75,108 @@ class NumpyStages:
         s = self.scores_rows.numpy()
         self.scores_rows.copy_(torch.from_numpy((s.T @ T).T.copy()))
 
-    def rank_gather(self, ci=0, nci=None):
+    def rank_gather(self, ci=0, nci=None, on_chunk=None, first_chunk=0):
         nci = self.kc - ci if nci is None else nci
         corr = self.scores_cols.numpy()
         for c in range(ci, ci + nci):
             self.y_cols[c] = torch.from_numpy(self.sortedX[c][oic.midpoint_index(corr[c])])
+        if nci > 0:
+            self._chunks(on_chunk, first_chunk)
 
     def status(self):
         return self._status
+
+
+class SharedMemoryTransport:
+    """CPU stand-in for CudaPeerTransport: every rank's "x" / "scols" / "srows" buffers live in POSIX
+    shared memory that the peers map (CUDA IPC's role), copies are NumPy slice assignments done at once
+    (the copy engines' role), the barrier is gloo's.  Same interface, same call sequence."""
+
+    NAMES = ("x", "scols", "srows")
+
+    def __init__(self, dist_, tag, shapes):
+        from multiprocessing import shared_memory
+        self.dist, self.rank, self.world = dist_, dist_.get_rank(), dist_.get_world_size()
+        self._own, self._peers, self.arr = [], [], {}
+        for name in self.NAMES:
+            size = max(8, int(np.prod(shapes[self.rank][name])) * 8)
+            self._own.append(shared_memory.SharedMemory(create=True, size=size, name=f"{tag}_{self.rank}_{name}"))
+        dist_.barrier()
+        for name in self.NAMES:
+            self.arr[name] = []
+            for g in range(self.world):
+                shm = shared_memory.SharedMemory(name=f"{tag}_{g}_{name}")
+                self._peers.append(shm)
+                self.arr[name].append(np.ndarray(shapes[g][name], dtype=np.float64, buffer=shm.buf))
+        for name in self.NAMES:
+            self.arr[name][self.rank][...] = 0.0
+        dist_.barrier()
+
+    def local(self):
+        return {name: self.arr[name][self.rank] for name in self.NAMES}
+
+    def _view(self, loc, count):
+        rank, what, off = loc
+        flat = what.numpy().reshape(-1) if rank is None else self.arr[what][rank].reshape(-1)
+        return flat[off:off + count]
+
+    def _copies(self, copies):
+        for dst, src, count in copies:
+            self._view(dst, count)[:] = self._view(src, count)
+
+    def compute_event(self):
+        return None
+
+    def push(self, copies, after, barrier=True):
+        self._copies(copies)
+        if barrier:
+            self.dist.barrier()
+
+    def pull(self, copies, after):
+        self.dist.barrier()
+        self._copies(copies)
+
+    def wait(self, ev):
+        pass
+
+    def close(self):
+        self.dist.barrier()
+        self.arr = {}
+        for shm in self._peers:
+            shm.close()
+        self.dist.barrier()
+        for shm in self._own:
+            shm.close()
+            shm.unlink()
+
+
+def _peer_worker(rank, world, port, n_local, k, seed, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        n_total = n_local * world
+        X = rng.normal(size=(n_total, k))
+        X[:, k - 1] = rng.poisson(2.0, n_total)
+        C = random_target(rng, k)
+        Xt = torch.from_numpy(np.ascontiguousarray(X[rank * n_local:(rank + 1) * n_local].T)).T
+        Yt = torch.empty_strided(Xt.shape, Xt.stride(), dtype=Xt.dtype)
+        blocks = column_blocks(k, world)
+        shapes = [{"x": (b - a, n_total), "scols": (b - a, n_total), "srows": (k, n_local)} for a, b in blocks]
+        tp = SharedMemoryTransport(dist, f"pblt{port}", shapes)
+        kc = blocks[rank][1] - blocks[rank][0]
+        stages = NumpyStages(n_local, n_total, k, kc, np.linalg.cholesky(C), buffers=tp.local())
+        runner = DistributedImanConover(n_local, k, C, dist, stages=stages, transport=tp)
+        for _ in range(2):  # twice: the second call finds every buffer in its end-of-call state
+            runner.run(Xt, Yt)
+        np.save(os.path.join(result_dir, f"y{rank}.npy"), Yt.numpy())
+        if rank == 0:
+            np.save(os.path.join(result_dir, "want.npy"), oic.iman_conover(X, C))
+        stages.x_cols = stages.y_cols = stages.scores_cols = stages.scores_rows = None
+        tp.close()
+    finally:
+        dist.destroy_process_group()
 
 
 def _worker(rank, world, port, n_local, k, seed, ties, result_dir):
@@ -108,6 +212,17 @@ def _free_port():
 @pytest.mark.parametrize("world,n_local,k,ties", [(2, 500, 5, False), (2, 301, 4, True), (3, 200, 2, False)])
 def test_rows_sharded_equals_single_process(tmp_path, world, n_local, k, ties):
     mp.spawn(_worker, args=(world, _free_port(), n_local, k, 7, ties, str(tmp_path)), nprocs=world, join=True)
+    want = np.load(tmp_path / "want.npy")
+    got = np.vstack([np.load(tmp_path / f"y{r}.npy") for r in range(world)])
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("world,n_local,k", [(2, 400, 5), (3, 150, 7), (3, 200, 2)])
+def test_peer_copy_choreography_equals_single_process(tmp_path, world, n_local, k):
+    """The peer-copy pipeline (pushes into the owners' buffers, row-chunk hook, barriers) with shared
+    memory standing in for CUDA IPC: exactly the single-process result, also with uneven column blocks
+    and with ranks that own no column."""
+    mp.spawn(_peer_worker, args=(world, _free_port(), n_local, k, 11, str(tmp_path)), nprocs=world, join=True)
     want = np.load(tmp_path / "want.npy")
     got = np.vstack([np.load(tmp_path / f"y{r}.npy") for r in range(world)])
     np.testing.assert_array_equal(got, want)

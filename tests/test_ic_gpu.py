@@ -131,6 +131,62 @@ def test_window_collisions_are_completed_in_tile():
     np.testing.assert_array_equal(got["result"], want)
 
 
+@pytest.mark.parametrize("group,attempts", [(31, 1), (32, 1), (33, 2), (48, 2)])
+def test_window_runs_around_the_in_tile_limit(group, attempts):
+    """Runs of `group` distinct keys that share one window value: up to 32 keys are re-ordered inside the
+    post-sort tile, longer ones raise the retry flag (exact 64-bit sort).  Bit-exact either way."""
+    rng = np.random.default_rng(14)
+    n, k = 120_000, 2
+    X = np.asfortranarray(rng.normal(size=(n, k)))
+    m = n // (2 * group)
+    base = np.exp(rng.uniform(-300, 300, m))
+    vals = (base[:, None] * (1.0 + np.arange(group)[None, :] * 2.0 ** -52)).ravel()
+    X[: m * group, 1] = rng.permutation(vals)
+    C = random_target(rng, k)
+    want = oic.iman_conover(X, C)
+    got = gpu_util.run_stages(X, C)
+    assert got["attempts"] == attempts and got["status"] == 0
+    np.testing.assert_array_equal(got["result"], want)
+
+
+def test_row_chunk_hook_delivers_the_same_scores_chunk_by_chunk():
+    """pbl_ic_plan_set_chunk_hook (the multi-GPU driver's hook): the scatter by row is enqueued per row
+    chunk, first_chunk first, the callback fires once per (column, chunk), results are unchanged."""
+    import ctypes as C_
+    from probabilit_b200 import _lib
+    from probabilit_b200.correlation import _IcPlan
+
+    lib = _lib.require_gpu()
+    rng = np.random.default_rng(15)
+    n, k, chunks = 1_500_000, 2, 4  # > 2^19 rows: grouped pairs, chunked delivery
+    X = np.asfortranarray(rng.normal(size=(n, k)))
+    plan = _IcPlan(n, k, 0)
+    plan.set_target(np.eye(k))
+    dX = gpu_util.DeviceArray(X)
+    chunk_rows = (n + chunks - 1) // chunks
+    try:
+        _lib.check(lib.pbl_ic_stage_begin(plan.handle, None))
+        _lib.check(lib.pbl_ic_stage_rank_scores(plan.handle, dX.ptr, 1, n, 0, k, None))
+        want = gpu_util.read_device(plan.buffer(0)[0], (n, k), order="F")
+        zeros = np.zeros((n, k), order="F")  # so that a row the chunked delivery missed would show
+        _lib.check(lib.pbl_memcpy_h2d(C_.c_void_p(plan.buffer(0)[0]), zeros.ctypes.data, zeros.nbytes, None))
+        _lib.check(lib.pbl_stream_synchronize(None))
+        seen = []
+        cb = _lib.CHUNK_FN(lambda col, g, user: seen.append((col, g)))
+        _lib.check(lib.pbl_ic_plan_set_chunk_hook(plan.handle, chunk_rows, 2, cb, None))
+        _lib.check(lib.pbl_ic_stage_begin(plan.handle, None))
+        for c in range(k):
+            _lib.check(lib.pbl_ic_stage_rank_scores(plan.handle, dX.ptr, 1, n, c, 1, None))
+        _lib.check(lib.pbl_ic_plan_set_chunk_hook(plan.handle, 0, 0, None, None))
+        got = gpu_util.read_device(plan.buffer(0)[0], (n, k), order="F")
+        assert _lib.check(lib.pbl_ic_stage_status(plan.handle, None)) == 0
+    finally:
+        dX.free()
+        plan.close()
+    assert seen == [(c, g) for c in range(k) for g in (2, 3, 0, 1)]
+    np.testing.assert_array_equal(got, want)
+
+
 def test_c_order_and_column_batches():
     from probabilit_b200 import ImanConover
 
