@@ -332,8 +332,16 @@ def run_ours(args, rank, world, local_rank):
         # D2H of the result, all inside the timed region (wall clock, max over ranks)
         nbytes = n * d * 8
         hx, hy = C.c_void_p(), C.c_void_p()
-        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hx), nbytes))
-        _lib.check(lib.pbl_host_malloc_pinned(C.byref(hy), nbytes))
+        ok = lib.pbl_host_malloc_pinned(C.byref(hx), nbytes) == 0 and lib.pbl_host_malloc_pinned(C.byref(hy), nbytes) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank takes the same branch
+        ok = bool(flag.item())
+    if world > 1 and args.e2e_steps > 0 and not ok:
+        for h in (hx, hy):
+            if h.value:
+                lib.pbl_host_free_pinned(h)
+        e2e = {"value": None, "unit": UNIT, "note": "pinned host buffers could not be allocated on every rank"}
+    if world > 1 and args.e2e_steps > 0 and ok:
         _lib.check(lib.pbl_memcpy_d2h(hx, C.c_void_p(X.data_ptr()), nbytes, sp))
         torch.cuda.synchronize()
 
