@@ -33,8 +33,9 @@ IC_BYTES_PER_SAMPLE_VAR = 456.0  # fixed algorithmic acc
 # 32-bit window reads the 8 B double instead of 12 B
 PASS_BYTES_PER_KEY = (3 * 24.0 + 20.0) / 4.0
 # measured DRAM traffic of one digit pass, dram__bytes_read.sum + dram__bytes_write.sum per key from the
-# `ncu --set full` capture profiles/r1_ncu_sort_kernels_summary.txt (8.47 GB for 3.2e8 keys)
-PASS_DRAM_BYTES_PER_KEY_NCU = 26.5
+# `ncu --set full` capture profiles/r1_ncu_sort_kernels_summary.txt (3.2e8 keys per launch: 7.44 GB for
+# the pass that reads the raw doubles, 8.74 GB for each of the other three -> 26.3 B/key on average)
+PASS_DRAM_BYTES_PER_KEY_NCU = 26.3
 
 
 def hbm_peak():
@@ -385,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
         "frac": (pass_gbs / peak) if pass_gbs else None,
         "traffic": PASS_DRAM_BYTES_PER_KEY_NCU * nkeys.value / max(nl.value, 1),
         "traffic_source": "ncu --set full capture at n=2e7 (profiles/r1_ncu_sort_kernels_summary.txt), "
-                          "26.5 B/key scaled to this launch's keys",
+                          "26.3 B/key (mean of the 4 passes) scaled to this launch's keys",
         "peak_source": peak_src,
         "launches_timed": nl.value, "avg_launch_ms": (pms.value / nl.value) if nl.value else None,
         "algorithmic_bytes_per_launch": PASS_BYTES_PER_KEY * nkeys.value / max(nl.value, 1),
