@@ -1,6 +1,6 @@
 import ctypes as C, json, os, sys
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from probabilit_b200 import _lib
 from probabilit_b200.correlation import _IcPlan
 n, k = int(float(sys.argv[1])), int(sys.argv[2])
