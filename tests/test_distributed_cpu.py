@@ -217,7 +217,7 @@ def test_rows_sharded_equals_single_process(tmp_path, world, n_local, k, ties):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("world,n_local,k", [(2, 400, 5), (3, 150, 7), (3, 200, 2)])
+@pytest.mark.parametrize("world,n_local,k", [(2, 400, 5), (3, 150, 7), (3, 200, 2), (4, 90, 16), (8, 40, 16)])
 def test_peer_copy_choreography_equals_single_process(tmp_path, world, n_local, k):
     """The peer-copy pipeline (pushes into the owners' buffers, row-chunk hook, barriers) with shared
     memory standing in for CUDA IPC: exactly the single-process result, also with uneven column blocks
