@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 
 #include "ndtri.cuh"
+#include "rank.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -102,8 +103,8 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
                  const PassPlan* __restrict__ plan, const uint64_t* __restrict__ kminmax,
                  int window_bits, uint32_t n, double* __restrict__ sortedX,
                  const double* __restrict__ vdw, uint32_t* __restrict__ flags, int col_base,
-                 int part_shift, uint32_t* __restrict__ status, uint32_t* __restrict__ tile_counter,
-                 int ntiles) {
+                 int part_shift, uint64_t* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                 int ntiles, uint32_t epoch) {
   extern __shared__ __align__(16) unsigned char psm[];
   uint64_t* s_raw = reinterpret_cast<uint64_t*>(psm);        // [kWin] keys as the sort left them
   uint64_t* s_key = s_raw + kWin;                            // [kWin] completed order
@@ -113,9 +114,13 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   uint32_t* s_end = s_start + kPostTile;                     // [kPostTile]
   uint32_t* s_w = s_end + kPostTile;                         // [kPostBlock / 32]
   uint32_t* s_lohi = s_w + kPostBlock / 32;                  // [2]
-  uint32_t* s_cnt = s_lohi + 4;                              // [kRadix] elements per destination window
+  uint32_t* s_cnt = s_lohi + 4;                              // [kRadix] (unused since the ballot ranking; kept for layout)
   uint32_t* s_bstart = s_cnt + kRadix;                       // [kRadix]
   uint32_t* s_goff = s_bstart + kRadix;                      // [kRadix]
+  // warp-private window counters of the fused partition: [16 warps][kRadix], on top of s_start / s_end
+  // (dead once step (3) has read them)
+  uint32_t* s_hist = s_start;
+  static_assert(2 * kPostTile == (kPostBlock / 32) * kRadix, "the counters alias s_start + s_end exactly");
   uint32_t* s_ticket = s_goff + kRadix;                      // [1] (+3 pad)
   uint32_t* s_mask = s_ticket + 4;                           // [kWin / 32] "same window as the slot to the left"
   KeyMap* s_map = reinterpret_cast<KeyMap*>(s_mask + kWin / 32);  // 8-byte aligned: all sizes above are
@@ -130,7 +135,6 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   // started (blockIdx order is not a scheduling guarantee)
   uint32_t tile = blockIdx.x;
   if (partition && tid == 0) *s_ticket = atomicAdd(&tile_counter[col], 1u);
-  if (partition && tid < kRadix) s_cnt[tid] = 0;
   if (tid == 32) *s_map = load_key_map(kminmax, col, window_bits);  // once per block, not per thread
   __syncthreads();
   if (partition) tile = *s_ticket;
@@ -343,25 +347,40 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
 
   // ---- (4) first half of the scatter by row, fused: group the tile's (row, value) pairs by
   //      destination window (row >> part_shift, <= 256 windows of L2 size) with a chained scan
-  //      between tiles, like partition_pass_kernel<SCATTER> but without its extra round trip of
-  //      the pairs through HBM.  No stable order is needed inside a window. ----
-  uint32_t slot[kPostItems];
+  //      between tiles, like the digit pass but without an extra round trip of the pairs through
+  //      HBM.  In-warp ranking by ballots against warp-private counters (rank.cuh) instead of returning
+  //      shared atomics on block-wide counters (~2 cycles per lane on B200: 43 % of this kernel). ----
+  if (tie) __syncthreads();  // step (3) has read s_start / s_end, which the counters overwrite
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  uint32_t* wh = s_hist + warp * kRadix;
+  {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(wh)[lane] = z;
+    reinterpret_cast<uint4*>(wh)[lane + 32] = z;
+  }
+  __syncwarp();
+  uint32_t dig[kPostItems], slot[kPostItems];
 #pragma unroll
-  for (int j = 0; j < kPostItems; ++j) {
-    uint32_t p = j * kPostBlock + tid;
-    slot[j] = 0;
-    if (p < nvalid) slot[j] = atomicAdd(&s_cnt[out_row[j] >> part_shift], 1u);
+  for (int j = 0; j < kPostItems; ++j) dig[j] = out_row[j] >> part_shift;
+  if (nvalid == (uint32_t)kPostTile) {
+    warp_rank_digits<kPostItems>(dig, wh, slot, lane);
+  } else {
+    bool valid[kPostItems];
+#pragma unroll
+    for (int j = 0; j < kPostItems; ++j) valid[j] = j * kPostBlock + tid < nvalid;
+    warp_rank_digits_masked<kPostItems>(dig, valid, wh, slot, lane);
   }
   __syncthreads();
   uint32_t cnt = 0, bin_start = 0;
-  uint32_t* st = status + (size_t)col * ntiles * kRadix;
+  uint64_t* st = status + (size_t)col * ntiles * kRadix;
+  const uint64_t tag = (uint64_t)epoch << 34;
   if (tid < kRadix) {
-    cnt = s_cnt[tid];
-    st_relaxed_u32(&st[(size_t)tile * kRadix + tid], cnt | (tile == 0 ? kFlagInclusive : kFlagPartial));
+#pragma unroll
+    for (int w = 0; w < kPostBlock / 32; ++w) cnt += s_hist[w * kRadix + tid];
+    st_relaxed_u64(&st[(size_t)tile * kRadix + tid], tag | (tile == 0 ? kStatusInclusive : kStatusPartial) | cnt);
   }
   {
     // exclusive scan of the 256 counts (threads >= 256 carry zeros)
-    const uint32_t lane = tid & 31, warp = tid >> 5;
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -372,14 +391,22 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
     __syncthreads();
     bin_start = incl - cnt;
     for (uint32_t w = 0; w < warp; ++w) bin_start += s_w[w];
-    if (tid < kRadix) s_bstart[tid] = bin_start;
+  }
+  if (tid < kRadix) {  // the counters become (window start in the tile + pairs of earlier warps in the window)
+    uint32_t run = bin_start;
+#pragma unroll
+    for (int w = 0; w < kPostBlock / 32; ++w) {
+      const uint32_t c = s_hist[w * kRadix + tid];
+      s_hist[w * kRadix + tid] = run;
+      run += c;
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kPostItems; ++j) {
     uint32_t p = j * kPostBlock + tid;
     if (p < nvalid) {
-      const uint32_t q = s_bstart[out_row[j] >> part_shift] + slot[j];
+      const uint32_t q = wh[dig[j]] + slot[j];
       s_pval[q] = out_val[j];
       s_prow[q] = out_row[j];
     }
@@ -387,33 +414,33 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
   if (tid < kRadix) {
     uint32_t excl = 0;
     if (tile != 0) {
-      constexpr int LB = 8;
+      constexpr int LB = 4;
       int64_t t = (int64_t)tile - 1;
       bool done = false;
       uint32_t spins = 0;
       while (!done) {
-        uint32_t pre[LB];
+        uint64_t pre[LB];
 #pragma unroll
         for (int i = 0; i < LB; ++i)
-          pre[i] = (t - i >= 0) ? ld_relaxed_u32(&st[(size_t)(t - i) * kRadix + tid]) : kFlagInclusive;
+          pre[i] = (t - i >= 0) ? ld_relaxed_u64(&st[(size_t)(t - i) * kRadix + tid]) : (tag | kStatusInclusive);
 #pragma unroll
         for (int i = 0; i < LB; ++i) {
           if (!done) {
-            const uint32_t w = pre[i];
-            if ((w & (kFlagInclusive | kFlagPartial)) == 0) {
+            const uint64_t w = pre[i];
+            if ((w >> 34) != (uint64_t)epoch || (w & (kStatusInclusive | kStatusPartial)) == 0) {
               if (++spins > (1u << 24)) {
                 atomicExch(&flags[kFlagWatchdog], 1u);
                 done = true;
               }
               break;
             }
-            excl += w & kValueMask;
+            excl += (uint32_t)w;
             --t;
-            if (w & kFlagInclusive) done = true;
+            if (w & kStatusInclusive) done = true;
           }
         }
       }
-      st_relaxed_u32(&st[(size_t)tile * kRadix + tid], ((excl + cnt) & kValueMask) | kFlagInclusive);
+      st_relaxed_u64(&st[(size_t)tile * kRadix + tid], tag | kStatusInclusive | (uint32_t)(excl + cnt));
     }
     const uint64_t b = (uint64_t)tid << part_shift;  // rows are a permutation of 0..n-1
     const uint32_t base = (uint32_t)(b < n ? b : n);
@@ -1061,12 +1088,16 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
     if (rc == kOk) rc = dev_alloc(ptr, count, p);
   };
   if (!p->rows_only) {
-    A(&p->sort.keysA, (size_t)cb * n);
-    A(&p->sort.keysB, (size_t)cb * n);
-    A(&p->sort.valsA, (size_t)cb * n);
-    A(&p->sort.valsB, (size_t)cb * n);
+    // + 16 B: the bulk copies of the digit pass read whole 16 B units around a tile (pass_tma.cuh)
+    A(&p->sort.keysA, (size_t)cb * n + 2);
+    A(&p->sort.keysB, (size_t)cb * n + 2);
+    A(&p->sort.valsA, (size_t)cb * n + 4);
+    A(&p->sort.valsB, (size_t)cb * n + 4);
     A(&p->sort.hist, (size_t)cb * kMaxPasses * kRadix);
     A((unsigned char**)&p->sort.status, sort_status_bytes(cb, (uint32_t)n));
+    if (rc == kOk && cudaMemset(p->sort.status, 0, sort_status_bytes(cb, (uint32_t)n)) != cudaSuccess) rc = kCudaError;
+    A(&p->sort.maps, (size_t)cb);
+    p->sort.epoch = &p->sort_epoch;
     A(&p->sort.tile_counter, (size_t)cb * (kMaxPasses + 1));
     A(&p->sort.kminmax, (size_t)cb * kMinMaxWords);
     A(&p->sort.plan, (size_t)cb);
@@ -1110,6 +1141,7 @@ void ic_plan_destroy(IcPlan* p) {
   cudaFree(p->sort.tile_counter);
   cudaFree(p->sort.plan);
   cudaFree(p->sort.kminmax);
+  cudaFree(p->sort.maps);
   cudaFree(p->flags);
   cudaFree(p->sortedX);
   cudaFree(p->vdw);
@@ -1194,18 +1226,19 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     PBL_RETURN_IF(post_sort_attr());
     int shift = 32, ntiles = 0;
     uint32_t* counter = nullptr;
+    uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), 1, p->use_lookback, kPostTile, &shift, &ntiles, &counter,
-                                  stream));
+                                  &epoch, stream));
     if (ranks_only)
       post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
-          ntiles);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
+          ntiles, epoch);
     else
       post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
-          ntiles);
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
+          ntiles, epoch);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, p->scores + (size_t)c * n, 1, (int64_t)n, stream));
   }
@@ -1283,12 +1316,13 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_RETURN_IF(post_sort_attr());
     int shift = 32, ntiles = 0;
     uint32_t* counter = nullptr;
+    uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), row_stride, p->use_lookback, kPostTile, &shift, &ntiles,
-                                  &counter, stream));
+                                  &counter, &epoch, stream));
     post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
         p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, p->sort.status, counter,
-        ntiles);
+        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
+        ntiles, epoch);
     PBL_LAUNCH_CHECK();
     PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, Y + (int64_t)c * col_stride, row_stride, col_stride,
                                       stream));

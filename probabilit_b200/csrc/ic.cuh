@@ -19,6 +19,7 @@ struct IcPlan {
   bool rows_only = false;  // no sort workspace: Gram / solve / transform stages only (multi-GPU row shard)
 
   SortBuffers sort;            // sized for col_batch columns
+  uint32_t sort_epoch = 0;     // tag of the last launch that used the look-back words (sort.cuh)
   double* sortedX = nullptr;   // [k][n]  np.sort(X[:,c])
   double* vdw = nullptr;       // [n] ndtri((p+1)/(n+1)): scores of an untied column, sorted order
   bool vdw_ready = false;

@@ -1,6 +1,8 @@
 // Batched per-column windowed onesweep LSD radix sort + scatter-by-row (see sort.cuh).
 #include "sort.cuh"
 
+#include "rank.cuh"
+
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -204,10 +206,12 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 // passes are no-ops, which buffer each pass reads).  One block of 256 threads per column.
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRadix)
-sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint32_t n, int npasses) {
+sort_scan_kernel(uint32_t* __restrict__ hist, PassPlan* __restrict__ plan, uint32_t n, int npasses,
+                 const uint64_t* __restrict__ kminmax, int window_bits, KeyMap* __restrict__ maps) {
   __shared__ uint32_t s_wsum[kRadix / 32];
   __shared__ int s_const[kMaxPasses];
   const int col = blockIdx.x;
+  if (threadIdx.x == 32) maps[col] = load_key_map(kminmax, col, window_bits);  // once per column, not per tile
   if (threadIdx.x < kMaxPasses) s_const[threadIdx.x] = 0;
   __syncthreads();
   for (int p = 0; p < npasses; ++p) {
@@ -339,6 +343,8 @@ __device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t
   asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(idx), "l"(base));
   *reinterpret_cast<uint32_t*>(addr) = v;
 }
+
+#include "pass_tma.cuh"
 
 #ifdef PBL_PASS_PROFILE
 // developer instrumentation (tools/pass_phases.py): cycle stamps of every 64th tile at the phase boundaries
@@ -763,6 +769,45 @@ int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
   return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
 }
 
+// PBL_PASS_IMPL=classic selects the one-tile-per-block kernel above (kept for A/B measurements and for
+// the no-look-back debug path); the default is the persistent bulk-async kernel (pass_tma.cuh)
+bool pass_impl_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PBL_PASS_IMPL");
+    v = (e && e[0] == 'c') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int next_epoch(const SortBuffers& buf, size_t status_bytes, cudaStream_t stream, uint32_t* out) {
+  // a fresh tag for every launch; the array is cleared once per 2^28 launches (and at allocation)
+  if (*buf.epoch >= (1u << 28)) {
+    PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, status_bytes, stream));
+    *buf.epoch = 0;
+  }
+  *out = ++*buf.epoch;
+  return kOk;
+}
+
+int launch_pass_tma(const PassArgs& a, int ncols, const SortBuffers& buf, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(pass_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    attr_set = true;
+  }
+  TmaArgs t;
+  t.p = a;
+  t.maps = buf.maps;
+  t.status64 = reinterpret_cast<uint64_t*>(buf.status);
+  t.ticket = a.tile_counter;
+  t.total_tiles = (uint32_t)ncols * (uint32_t)a.ntiles;
+  PBL_RETURN_IF(next_epoch(buf, sort_status_bytes(ncols, a.n), stream, &t.epoch));
+  const unsigned grid = (unsigned)std::min<size_t>((size_t)2 * num_sms(), (size_t)t.total_tiles);
+  pass_tma_kernel<<<grid, kTmaThreads, kTmaSmemBytes, stream>>>(t);
+  return kOk;
+}
+
 struct PassEvent {
   cudaEvent_t start, stop;
   int64_t keys;
@@ -815,7 +860,7 @@ size_t sort_status_bytes(int ncols, uint32_t n) {
   // the fused post-sort partition (ic.cu) works on 2048-element tiles: size for the smaller tile
   size_t tile = std::min<size_t>((size_t)sort_tile_size(), 2048);
   size_t ntiles = ((size_t)n + tile - 1) / tile;
-  return (size_t)ncols * ntiles * kRadix * sizeof(uint32_t);
+  return (size_t)ncols * ntiles * kRadix * sizeof(uint64_t);  // 64-bit epoch-tagged words (pass_tma.cuh)
 }
 
 int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, uint32_t n,
@@ -861,7 +906,7 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
                                                           buf.kminmax, window_bits);
     PBL_LAUNCH_CHECK();
   }
-  sort_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.hist, buf.plan, n, npasses);
+  sort_scan_kernel<<<ncols, kRadix, 0, stream>>>(buf.hist, buf.plan, n, npasses, buf.kminmax, window_bits, buf.maps);
   PBL_LAUNCH_CHECK();
 
   const size_t status_bytes = sort_status_bytes(ncols, n);
@@ -883,8 +928,11 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
   a.window_bits = window_bits;
   a.ntiles = ntiles;
   a.use_lookback = use_lookback ? 1 : 0;
+  const bool tma = use_lookback && pass_impl_tma();
   for (int pass = 0; pass < npasses; ++pass) {
-    if (use_lookback) {
+    if (tma) {
+      // epoch-tagged look-back words: nothing to clear
+    } else if (use_lookback) {
       PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, status_bytes, stream));
     } else {
       tile_hist_kernel<256><<<dim3(ntiles, ncols), 256, 0, stream>>>(
@@ -903,7 +951,12 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
       ev.keys = (int64_t)n * ncols;
       cudaEventRecord(ev.start, stream);
     }
-    PBL_RETURN_IF(launch_pass_cfg<false>(a, ncols, stream));
+    if (tma) {
+      a.ntiles = (int)(((size_t)n + kTmaTile - 1) / kTmaTile);
+      PBL_RETURN_IF(launch_pass_tma(a, ncols, buf, stream));
+    } else {
+      PBL_RETURN_IF(launch_pass_cfg<false>(a, ncols, stream));
+    }
     if (g_profile) {
       cudaEventRecord(ev.stop, stream);
       g_events.push_back(ev);
@@ -925,15 +978,16 @@ static int scatter_shift_for(uint32_t n) {
 // scatter_prepare() returned a shift < 32; this kernel delivers value -> out[row].
 int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_stride, bool use_lookback,
                     int consumer_tile, int* shift_out, int* ntiles_out, uint32_t** tile_counter_out,
-                    cudaStream_t stream) {
+                    uint32_t* epoch_out, cudaStream_t stream) {
   int shift = scatter_shift_for(n);
   if (!(use_lookback && row_stride == 1)) shift = 32;
   const int ntiles = (int)(((size_t)n + consumer_tile - 1) / consumer_tile);
   *shift_out = shift;
   *ntiles_out = ntiles;
   *tile_counter_out = buf.tile_counter + (size_t)kMaxPasses * ncols;
+  *epoch_out = 0;
   if (shift < 32) {
-    PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, (size_t)ncols * ntiles * kRadix * sizeof(uint32_t), stream));
+    PBL_RETURN_IF(next_epoch(buf, sort_status_bytes(ncols, n), stream, epoch_out));
     PBL_CUDA_CHECK(cudaMemsetAsync(*tile_counter_out, 0, (size_t)ncols * 4, stream));
   }
   return kOk;

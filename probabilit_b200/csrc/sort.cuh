@@ -45,6 +45,21 @@ constexpr uint32_t kMaxSortN = 0x3FFFFFFFu;  // 30-bit counts in the look-back w
 constexpr uint32_t kRowMask = 0x3FFFFFFFu;   // payload bits that hold the row
 constexpr uint32_t kNegZeroFlag = 0x80000000u;
 
+// Look-back words of the chained scans (digit pass, fused row-window partition) are 64-bit and tagged
+// with the EPOCH of the launch that wrote them: [epoch:30 | flag:2 | count:32].  A word from an earlier
+// launch reads as "not published", so the array is never cleared between launches (it used to be a
+// 0.4-0.8 GB memset before each of the 10 launches of a call) and counts are full 32-bit.
+constexpr uint64_t kStatusInclusive = 2ull << 32;
+constexpr uint64_t kStatusPartial = 1ull << 32;
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // error_flag[] slots shared by the sort and its consumers
 enum SortFlag : int {
   kFlagWatchdog = 0,    // look-back spin limit hit
@@ -149,7 +164,9 @@ struct SortBuffers {
   uint32_t* tile_counter = nullptr;  // [8 passes + 1 scatter pass][ncols]
   PassPlan* plan = nullptr;          // [ncols]
   uint64_t* kminmax = nullptr;       // [ncols][4], see KeyMap
+  KeyMap* maps = nullptr;            // [ncols] the window map of every column (written by sort_scan_kernel)
   uint32_t* error_flag = nullptr;    // [8], see SortFlag
+  uint32_t* epoch = nullptr;         // host counter: launches that have used `status` with epoch-tagged words
 };
 
 // tile size of the partition kernel in use (PBL_SORT_CFG selects the instantiation)
@@ -175,11 +192,11 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
 // pairs the sort's consumer staged in the "other" ping-pong buffer (vals[other] / keys[other]).
 // For long columns the consumer first groups the pairs into <= 256 L2-sized row windows (a fused
 // partition step, chained scan between its tiles of `consumer_tile` elements): scatter_prepare
-// returns the window shift (32 = no grouping), the tile count and the ticket counter, and clears
-// the look-back words.  scatter_rows then writes every 128 B line of the output once, from L2.
+// returns the window shift (32 = no grouping), the tile count, the ticket counter and the epoch tag of
+// the launch's look-back words.  scatter_rows then writes every 128 B line of the output once, from L2.
 int scatter_prepare(uint32_t n, int ncols, const SortBuffers& buf, int64_t row_stride, bool use_lookback,
                     int consumer_tile, int* shift_out, int* ntiles_out, uint32_t** tile_counter_out,
-                    cudaStream_t stream);
+                    uint32_t* epoch_out, cudaStream_t stream);
 // [pos_begin, pos_end): the staged positions to deliver.  With grouped pairs (shift < 32) the pairs of
 // rows [a << shift, b << shift) are exactly the positions [a << shift, b << shift), so a caller can
 // deliver the output row range by row range (the multi-GPU driver sends each range off as it completes).

@@ -351,6 +351,97 @@ def test_full_size_properties():
     assert np.max(np.abs(spearman - want)) < 5e-3, np.max(np.abs(spearman - want))
 
 
+def config3_inputs(n, d, seed=0):
+    """BASELINE.json configs[2] as SURVEY.md section 8(d) C3 spells it out: scrambled Sobol' quantiles
+    (SciPy, `seed`) pushed through marginals cycling norm(1, 2) / triang(0.5) / gamma(a=2) by column."""
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "balance properties of Sobol' points require n to be a power of 2"
+        q = sp.stats.qmc.Sobol(d, seed=seed, scramble=True).random(n)
+    X = np.empty((n, d), order="F")
+    for c in range(d):
+        dist = (sp.stats.norm(loc=1, scale=2), sp.stats.triang(0.5), sp.stats.gamma(a=2))[c % 3]
+        X[:, c] = dist.ppf(q[:, c])
+    return X
+
+
+def test_config3_at_1e7_rows_is_bit_exact():
+    """The headline configuration at the largest size the CPU oracle finishes in about a minute
+    (N = 1e7, d = 16; SURVEY.md section 7, hard part 1: exact equality is expected up to N = 1e7):
+    reference generator + SciPy ppfs on the host, output compared entry for entry."""
+    import os
+
+    from bench import target_matrix
+    from probabilit_b200 import ImanConover
+
+    n = int(float(os.environ.get("PBL_TEST_EXACT_ROWS", "1e7")))
+    d = 16
+    X = config3_inputs(n, d)
+    assert np.isfinite(X).all()
+    Ct = target_matrix(d)
+    got = ImanConover().set_target(Ct)(X)
+    want = oic.iman_conover(X, Ct)
+    assert got.flags.f_contiguous and got.dtype == want.dtype
+    np.testing.assert_array_equal(got, want)
+
+
+def test_full_size_strided_columns_against_numpy():
+    """N = 1e8, d = 16 (PBL_TEST_FULL_ROWS overrides), stage by stage on the device, two columns downloaded
+    and re-derived on the host with NumPy (SURVEY.md section 7, hard part 1):  sortedX == np.sort(X[:, c]);
+    scores within 4 ulp of ndtri(rankdata / (N + 1)); and the final index is exactly the reference's
+    `rankdata(correlated).astype(int) - 1` of the DEVICE's correlated scores, i.e.
+    Y[:, c] == np.sort(X[:, c])[midpoint_index(correlated[:, c])]  (correlation.py:419-423)."""
+    import ctypes as C
+    import os
+
+    import torch
+    from scipy.special import ndtri
+
+    from bench import make_workload_device, target_matrix
+    from probabilit_b200 import _lib
+    from probabilit_b200.correlation import _IcPlan
+
+    n = int(float(os.environ.get("PBL_TEST_FULL_ROWS", "1e8")))
+    d = 16
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * d * 8 * 9:
+        pytest.skip("not enough free device memory for the full-size case")
+    lib = _lib.require_gpu()
+    X = make_workload_device(n, d, seed=7, torch=torch)
+    Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
+    plan = _IcPlan(n, d, torch.cuda.current_device())
+    plan.set_target(np.linalg.cholesky(target_matrix(d)))
+    h, sp_ = plan.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cols = (4, 11)  # a triang and a gamma marginal (column 0 takes the T[0,0] == 1 shortcut elsewhere)
+
+    def grab(buffer_index):
+        base = plan.buffer(buffer_index)[0]
+        return [gpu_util.read_device(base + c * n * 8, (n,)) for c in cols]
+
+    chk = _lib.check
+    chk(lib.pbl_ic_stage_begin(h, sp_))
+    chk(lib.pbl_ic_stage_rank_scores(h, X.data_ptr(), 1, n, 0, d, sp_))
+    scores, sorted_x = grab(0), grab(1)
+    chk(lib.pbl_ic_stage_gram(h, sp_))
+    chk(lib.pbl_ic_stage_solve(h, n, sp_))
+    chk(lib.pbl_ic_stage_transform(h, sp_))
+    correlated = grab(0)
+    chk(lib.pbl_ic_stage_rank_gather(h, Y.data_ptr(), 1, n, 0, d, sp_))
+    assert chk(lib.pbl_ic_stage_status(h, sp_)) == 0
+    for i, c in enumerate(cols):
+        x = X[:, c].cpu().numpy()
+        ranks, order = oic.average_ranks(x)
+        np.testing.assert_array_equal(sorted_x[i], x[order])
+        want_scores = ndtri(ranks / (n + 1))
+        assert gpu_util.ulp_diff(scores[i], want_scores).max() <= 4.0
+        del ranks, order, want_scores
+        idx = oic.midpoint_index(correlated[i])
+        np.testing.assert_array_equal(Y[:, c].cpu().numpy(), sorted_x[i][idx])
+        del idx, x
+    plan.close()
+
+
 @pytest.mark.parametrize("n,k", [(3000, 100), (2500, 257)])
 def test_wide_problem_uses_grid_cholesky(n, k):
     """k > 64: correlation / Cholesky / T are computed by the cooperative multi-block kernel."""
