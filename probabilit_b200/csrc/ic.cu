@@ -21,7 +21,7 @@
 #include <cooperative_groups.h>
 
 #include "ndtri.cuh"
-#include "rank.cuh"
+#include "tile_pipeline.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -457,6 +457,19 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
       stage[g] = s_pval[p];
     }
   }
+}
+
+#include "post_tma.cuh"
+
+// PBL_POST_IMPL=classic selects post_sort_kernel above (kept for A/B measurements and for the no-look-back
+// debug path); the default is the persistent bulk-async kernel (post_tma.cuh)
+bool post_impl_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PBL_POST_IMPL");
+    v = (e && e[0] == 'c') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // ======================================================================================
@@ -1170,6 +1183,41 @@ int ic_plan_set_target(IcPlan* p, const double* P_lower_host) {
 // ======================================================================================
 static SortBuffers sort_view(const IcPlan* p) { return p->sort; }
 
+template <int MODE>
+static int launch_post_tma(IcPlan* p, int c, int nb, int shift, uint32_t epoch, uint32_t* counter,
+                           cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(post_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kPostTmaSmemBytes));
+    attr_set = true;
+  }
+  PostArgs a;
+  a.keysA = p->sort.keysA;
+  a.keysB = p->sort.keysB;
+  a.valsA = p->sort.valsA;
+  a.valsB = p->sort.valsB;
+  a.plan = p->sort.plan;
+  a.maps = p->sort.maps;
+  a.sortedX = p->sortedX + (size_t)c * p->n;
+  a.vdw = p->vdw;
+  a.flags = p->flags;
+  a.status64 = reinterpret_cast<uint64_t*>(p->sort.status);
+  a.ticket = counter;
+  a.n = (uint32_t)p->n;
+  a.ntiles = (uint32_t)((p->n + kTile - 1) / kTile);
+  a.total_tiles = a.ntiles * (uint32_t)nb;
+  a.epoch = epoch;
+  a.col_base = c;
+  a.part_shift = shift;
+  a.ncols_interleave = tickets_interleaved() ? (uint32_t)nb : 0u;
+  PBL_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
+  const unsigned grid = (unsigned)std::min<size_t>((size_t)2 * num_sms(), (size_t)a.total_tiles);
+  post_tma_kernel<MODE><<<grid, kTileThreads, kPostTmaSmemBytes, stream>>>(a);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
 static int post_sort_attr() {
   static bool done = false;
   if (!done) {
@@ -1229,17 +1277,23 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), 1, p->use_lookback, kPostTile, &shift, &ntiles, &counter,
                                   &epoch, stream));
-    if (ranks_only)
-      post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
-          p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
-          ntiles, epoch);
-    else
-      post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
-          p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
-          ntiles, epoch);
-    PBL_LAUNCH_CHECK();
+    if (p->use_lookback && post_impl_tma()) {
+      if (ranks_only)
+        PBL_RETURN_IF(launch_post_tma<2>(p, c, nb, shift, epoch, counter, stream));
+      else
+        PBL_RETURN_IF(launch_post_tma<0>(p, c, nb, shift, epoch, counter, stream));
+    } else {
+      uint64_t* st64 = reinterpret_cast<uint64_t*>(p->sort.status);
+      if (ranks_only)
+        post_sort_kernel<2><<<grid, kPostBlock, kPostSmem, stream>>>(
+            p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+            p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, st64, counter, ntiles, epoch);
+      else
+        post_sort_kernel<0><<<grid, kPostBlock, kPostSmem, stream>>>(
+            p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+            p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, st64, counter, ntiles, epoch);
+      PBL_LAUNCH_CHECK();
+    }
     PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, p->scores + (size_t)c * n, 1, (int64_t)n, stream));
   }
   return kOk;
@@ -1319,11 +1373,15 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), row_stride, p->use_lookback, kPostTile, &shift, &ntiles,
                                   &counter, &epoch, stream));
-    post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
-        p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
-        p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift, reinterpret_cast<uint64_t*>(p->sort.status), counter,
-        ntiles, epoch);
-    PBL_LAUNCH_CHECK();
+    if (p->use_lookback && post_impl_tma()) {
+      PBL_RETURN_IF(launch_post_tma<1>(p, c, nb, shift, epoch, counter, stream));
+    } else {
+      post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
+          p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
+          p->window_bits, n, p->sortedX + (size_t)c * n, p->vdw, p->flags, c, shift,
+          reinterpret_cast<uint64_t*>(p->sort.status), counter, ntiles, epoch);
+      PBL_LAUNCH_CHECK();
+    }
     PBL_RETURN_IF(scatter_rows_hooked(p, c, nb, shift, Y + (int64_t)c * col_stride, row_stride, col_stride,
                                       stream));
   }

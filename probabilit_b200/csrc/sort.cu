@@ -1,7 +1,7 @@
 // Batched per-column windowed onesweep LSD radix sort + scatter-by-row (see sort.cuh).
 #include "sort.cuh"
 
-#include "rank.cuh"
+#include "tile_pipeline.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -332,17 +332,6 @@ struct PassArgs {
   int ntiles;
   int use_lookback;
 };
-
-__device__ __forceinline__ void st_u64_at(uint64_t* base, uint32_t idx, uint64_t v) {
-  uint64_t addr;
-  asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(idx), "l"(base));
-  *reinterpret_cast<uint64_t*>(addr) = v;
-}
-__device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t v) {
-  uint64_t addr;
-  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(idx), "l"(base));
-  *reinterpret_cast<uint32_t*>(addr) = v;
-}
 
 #include "pass_tma.cuh"
 
@@ -780,6 +769,18 @@ bool pass_impl_tma() {
   return v == 1;
 }
 
+}  // namespace
+// PBL_TICKET_ORDER=column: tiles are handed out column after column (A/B measurements); default: interleaved
+bool tickets_interleaved() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PBL_TICKET_ORDER");
+    v = (e && e[0] == 'c') ? 0 : 1;
+  }
+  return v == 1;
+}
+namespace {
+
 int next_epoch(const SortBuffers& buf, size_t status_bytes, cudaStream_t stream, uint32_t* out) {
   // a fresh tag for every launch; the array is cleared once per 2^28 launches (and at allocation)
   if (*buf.epoch >= (1u << 28)) {
@@ -802,9 +803,10 @@ int launch_pass_tma(const PassArgs& a, int ncols, const SortBuffers& buf, cudaSt
   t.status64 = reinterpret_cast<uint64_t*>(buf.status);
   t.ticket = a.tile_counter;
   t.total_tiles = (uint32_t)ncols * (uint32_t)a.ntiles;
+  t.ncols_interleave = tickets_interleaved() ? (uint32_t)ncols : 0u;
   PBL_RETURN_IF(next_epoch(buf, sort_status_bytes(ncols, a.n), stream, &t.epoch));
   const unsigned grid = (unsigned)std::min<size_t>((size_t)2 * num_sms(), (size_t)t.total_tiles);
-  pass_tma_kernel<<<grid, kTmaThreads, kTmaSmemBytes, stream>>>(t);
+  pass_tma_kernel<<<grid, kTileThreads, kTmaSmemBytes, stream>>>(t);
   return kOk;
 }
 

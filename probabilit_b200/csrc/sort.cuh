@@ -169,6 +169,8 @@ struct SortBuffers {
   uint32_t* epoch = nullptr;         // host counter: launches that have used `status` with epoch-tagged words
 };
 
+bool tickets_interleaved();
+
 // tile size of the partition kernel in use (PBL_SORT_CFG selects the instantiation)
 int sort_tile_size();
 size_t sort_status_bytes(int ncols, uint32_t n);
