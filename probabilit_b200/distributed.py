@@ -91,10 +91,21 @@ class CudaStages:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
 
+    def _note(self, status, what):
+        """A CUDA / internal failure (status 4 / 5) of a stage call is REMEMBERED, not raised: raising here
+        would take this rank out of the choreography while its peers block in the next collective.  It
+        comes back through status(), is agreed across the ranks and is raised by all of them together."""
+        if status in (_lib.STATUS_CUDA, _lib.STATUS_INTERNAL) and self.failure is None:
+            self.failure = (int(status), f"{what} failed: {_lib.last_error()}")
+        return status
+
+    failure = None
+
     def begin(self):
+        self.failure = None
         for p in (self.row_plan, self.sort_plan):
             if p is not None:
-                _lib.check(self.lib.pbl_ic_stage_begin(p.handle, self._stream()))
+                self._note(self.lib.pbl_ic_stage_begin(p.handle, self._stream()), "pbl_ic_stage_begin")
 
     class _ChunkHook:
         """Scope of the row-chunk hook (pbl_ic_plan_set_chunk_hook): on_chunk(g) is called as soon as the
@@ -127,29 +138,33 @@ class CudaStages:
         nci = self.kc - ci if nci is None else nci
         if nci > 0:
             with self._ChunkHook(self, on_chunk, first_chunk):
-                _lib.check(self.lib.pbl_ic_stage_rank_scores(
-                    self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
+                self._note(self.lib.pbl_ic_stage_rank_scores(
+                    self.sort_plan.handle, self.x_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()),
+                    "pbl_ic_stage_rank_scores")
 
     def gram_partial(self):  # scores_rows -> gram, colsum (local partial sums)
-        _lib.check(self.lib.pbl_ic_stage_gram(self.row_plan.handle, self._stream()))
+        self._note(self.lib.pbl_ic_stage_gram(self.row_plan.handle, self._stream()), "pbl_ic_stage_gram")
 
     def solve_and_transform(self):  # gram/colsum (global) -> T ; scores_rows <- scores_rows @ T
-        _lib.check(self.lib.pbl_ic_stage_solve(self.row_plan.handle, self.n_total, self._stream()))
-        _lib.check(self.lib.pbl_ic_stage_transform(self.row_plan.handle, self._stream()))
+        self._note(self.lib.pbl_ic_stage_solve(self.row_plan.handle, self.n_total, self._stream()), "pbl_ic_stage_solve")
+        self._note(self.lib.pbl_ic_stage_transform(self.row_plan.handle, self._stream()), "pbl_ic_stage_transform")
 
     def rank_gather(self, ci=0, nci=None, on_chunk=None, first_chunk=0):
         """scores_cols (correlated) -> y_cols"""
         nci = self.kc - ci if nci is None else nci
         if nci > 0:
             with self._ChunkHook(self, on_chunk, first_chunk):
-                _lib.check(self.lib.pbl_ic_stage_rank_gather(
-                    self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()))
+                self._note(self.lib.pbl_ic_stage_rank_gather(
+                    self.sort_plan.handle, self.y_cols.data_ptr(), 1, self.n_total, ci, nci, self._stream()),
+                    "pbl_ic_stage_rank_gather")
 
     def status(self):
         st = 0
         for p in (self.row_plan, self.sort_plan):
             if p is not None:
-                st = max(st, _lib.check(self.lib.pbl_ic_stage_status(p.handle, self._stream())))
+                st = max(st, self._note(self.lib.pbl_ic_stage_status(p.handle, self._stream()), "pbl_ic_stage_status"))
+        if self.failure is not None:
+            st = max(st, self.failure[0])
         return st
 
     def close(self):
@@ -355,6 +370,29 @@ class DistributedImanConover:
         for r in range(self.rounds):
             self._wait(self._round(r, cols_buf=cols_buf, rows_buf=rows_buf, to_cols=False))
 
+    def _reduce_gram(self):
+        """Global Gram and column sums from the ranks' partials: gathered, then summed IN RANK ORDER by
+        every rank (a fixed reduction order, so the result does not depend on the
+        collective's algorithm, tree or chunking and is identical on every rank and from run to run).
+        k*k + k doubles per rank: latency-bound either way."""
+        st, dist = self.st, self.dist
+        torch_mod = st.torch
+        part = torch_mod.cat([st.gram, st.colsum])
+        parts = [torch_mod.empty_like(part) for _ in range(self.world)]
+        dist.all_gather(parts, part)
+        total = parts[0].clone()
+        for g in range(1, self.world):
+            total += parts[g]
+        st.gram.copy_(total[:st.gram.numel()])
+        st.colsum.copy_(total[st.gram.numel():])
+
+    def _finish(self, status):
+        """Agreed status -> the same outcome on every rank."""
+        if status in (_lib.STATUS_CUDA, _lib.STATUS_INTERNAL):
+            mine = getattr(self.st, "failure", None)
+            raise _lib.PblError(mine[1] if mine else "a peer rank failed inside the multi-GPU Iman-Conover call")
+        _raise_for_status(status)
+
     # ------------------------------------------------------------------ the transform
     def run(self, X_local, Y_local):
         """Y_local <- Iman-Conover(X) restricted to this rank's rows.  Raises like the reference."""
@@ -384,8 +422,7 @@ class DistributedImanConover:
                 self._wait(reqs)
             self._mark("wait scores back")
             st.gram_partial()                                # 4
-            dist.all_reduce(st.gram)
-            dist.all_reduce(st.colsum)
+            self._reduce_gram()
             st.solve_and_transform()                         # 5
             self._mark("gram+allreduce+transform")
             # 6-8: correlated scores rows -> columns, rank + gather, Y columns -> rows, pipelined
@@ -406,7 +443,7 @@ class DistributedImanConover:
             self._mark("status")
             if status != 6:  # PBL_RETRY: some rank switched to the exact 64-bit sort; run again
                 break
-        _raise_for_status(status)
+        self._finish(status)
         return Y_local
 
     # ------------------------------------------------------------------ the transform, peer copies
@@ -448,8 +485,7 @@ class DistributedImanConover:
             tp.wait(tp.push([], tp.compute_event(), barrier=True))
             self._mark("wait scores back")
             st.gram_partial()                                # 4
-            dist.all_reduce(st.gram)
-            dist.all_reduce(st.colsum)
+            self._reduce_gram()
             st.solve_and_transform()                         # 5
             self._mark("gram+allreduce+transform")
             # 6-8: correlated scores rows -> columns (push), rank + gather, Y columns -> rows (pull)
@@ -476,7 +512,7 @@ class DistributedImanConover:
             self._mark("status")
             if status != 6:
                 break
-        _raise_for_status(status)
+        self._finish(status)
         return Y_local
 
     def _agree(self, status):
@@ -485,9 +521,12 @@ class DistributedImanConover:
         if torch_mod is None:
             import torch as torch_mod
         dev = "cuda" if torch_mod.cuda.is_available() and self.dist.get_backend() == "nccl" else "cpu"
-        t = torch_mod.tensor([int(status)], dtype=torch_mod.int32, device=dev)
+        # a failure (4 / 5) on any rank outranks a retry request (6) of another
+        failed = status in (_lib.STATUS_CUDA, _lib.STATUS_INTERNAL)
+        t = torch_mod.tensor([int(status) + (10 if failed else 0)], dtype=torch_mod.int32, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return int(t.item())
+        agreed = int(t.item())
+        return agreed - 10 if agreed >= 10 else agreed
 
     def close(self):
         if self.tp is not None:

@@ -203,6 +203,59 @@ def _worker(rank, world, port, n_local, k, seed, ties, result_dir):
         dist.destroy_process_group()
 
 
+class FailingStages(NumpyStages):
+    """A stage call fails (CUDA / internal error) on ONE rank only."""
+
+    def __init__(self, *args, fail=False, **kw):
+        super().__init__(*args, **kw)
+        self.fail = fail
+        self.failure = None
+
+    def rank_gather(self, *args, **kw):
+        super().rank_gather(*args, **kw)
+        if self.fail:
+            self.failure = (5, "injected failure")  # what CudaStages._note records
+
+    def status(self):
+        return 5 if self.failure else super().status()
+
+
+def _failing_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from probabilit_b200._lib import PblError
+
+        rng = np.random.default_rng(3)
+        n_local, k = 120, 4
+        X = rng.normal(size=(n_local * world, k))
+        C = random_target(rng, k)
+        Xt = torch.from_numpy(np.ascontiguousarray(X[rank * n_local:(rank + 1) * n_local].T)).T
+        Yt = torch.empty_strided(Xt.shape, Xt.stride(), dtype=Xt.dtype)
+        a, b = column_blocks(k, world)[rank]
+        stages = FailingStages(n_local, n_local * world, k, b - a, np.linalg.cholesky(C), fail=(rank == 1))
+        outcome = "no exception"
+        try:
+            DistributedImanConover(n_local, k, C, dist, stages=stages).run(Xt, Yt)
+        except PblError as e:
+            outcome = f"PblError: {e}"
+        with open(os.path.join(result_dir, f"outcome{rank}.txt"), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_failure_on_one_rank_is_raised_by_all_ranks(tmp_path):
+    """A CUDA / internal failure of a stage on one rank must not leave the others blocked in a collective:
+    it is folded into the agreed status and every rank raises PblError after the collective."""
+    world = 3
+    mp.spawn(_failing_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outcomes = [(tmp_path / f"outcome{r}.txt").read_text() for r in range(world)]
+    assert all(o.startswith("PblError") for o in outcomes), outcomes
+    assert "injected failure" in outcomes[1] and "peer rank failed" in outcomes[0]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
