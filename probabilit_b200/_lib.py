@@ -9,6 +9,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libprobabilit_b200.so")
+# developer aid: A/B a differently compiled build of the same sources (tools/ only; the product path is LIB_PATH)
+LIB_PATH = os.environ.get("PBL_LIB", LIB_PATH)
 
 STATUS_OK, STATUS_NOT_PD, STATUS_NON_FINITE, STATUS_BAD_SHAPE, STATUS_CUDA, STATUS_INTERNAL = range(6)
 

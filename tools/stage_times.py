@@ -1,6 +1,6 @@
 """Per-stage device times of the Iman-Conover pipeline (CUDA events on the launching stream).
 
-    python tools/stage_times.py [N] [K] [reps]
+    python tools/stage_times.py [N] [K] [reps] [col_batch]
 """
 import ctypes as C
 import json
@@ -19,6 +19,7 @@ def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    col_batch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     lib = _lib.require_gpu()
     torch.cuda.init()
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -27,7 +28,7 @@ def main():
     rng = np.random.default_rng(0)
     A = rng.normal(size=(2 * k, k))
     Ct = 0.9 * np.corrcoef(A, rowvar=False) + 0.1 * np.eye(k)
-    plan = _IcPlan(n, k, 0)
+    plan = _IcPlan(n, k, 0, col_batch)
     plan.set_target(np.linalg.cholesky(Ct))
     h = plan.handle
     s = torch.cuda.current_stream().cuda_stream
