@@ -213,12 +213,25 @@ __global__ void __launch_bounds__(kTileThreads, 2) pass_tma_kernel(const TmaArgs
   __syncthreads();
   for (uint32_t it = 0;; ++it) {
     const uint32_t s = it & 1u;
+#ifdef PBL_TILE_STATS
+    const long long w0 = clock64();
+#endif
     mbar_wait(sm.full(s), (it >> 1) & 1u, a.p.error_flag);
+#ifdef PBL_TILE_STATS
+    const long long w1 = clock64();
+#endif
     const TmaTicket tk = sm.tk[s];
     if ((tk.mode_off & 255u) == kModeEnd) break;
     if (tk.nvalid == (uint32_t)kTmaTile)
       tma_tile<true>(a, sm, s, tk);
     else
       tma_tile<false>(a, sm, s, tk);
+#ifdef PBL_TILE_STATS
+    if (tid == 0) {
+      atomicAdd(&g_tile_stats[0], 1ull);
+      atomicAdd(&g_tile_stats[4], (unsigned long long)(clock64() - w1));
+      atomicAdd(&g_tile_stats[5], (unsigned long long)(w1 - w0));
+    }
+#endif
   }
 }

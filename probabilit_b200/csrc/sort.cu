@@ -834,6 +834,19 @@ extern "C" __attribute__((visibility("default"))) int pbl_debug_pass_stamps(long
 namespace pbl {
 #endif
 
+#ifdef PBL_TILE_STATS
+}  // namespace pbl
+// developer instrumentation: read and clear the tile statistics (tile_pipeline.cuh)
+extern "C" __attribute__((visibility("default"))) int pbl_debug_tile_stats(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, pbl::g_tile_stats, 8 * sizeof(unsigned long long));
+  unsigned long long zero[8] = {0};
+  cudaMemcpyToSymbol(pbl::g_tile_stats, zero, sizeof(zero));
+  return 0;
+}
+namespace pbl {
+#endif
+
 void sort_profile_enable(bool on) { g_profile = on; }
 
 void sort_profile_read(int64_t* launches, double* total_ms, int64_t* keys) {

@@ -69,6 +69,14 @@ __device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t
   *reinterpret_cast<uint32_t*>(addr) = v;
 }
 
+#ifdef PBL_TILE_STATS
+// developer instrumentation (tools/tile_stats.py; build with PBL_EXTRA_NVCC_FLAGS=-DPBL_TILE_STATS):
+// per-launch totals taken by thread 0 -- [0] tiles of the digit pass, [1] look-back words consumed,
+// [2] polls that found an unpublished word, [3] cycles in the look-back, [4] cycles from "tile data landed"
+// to the end of the tile, [5] cycles waiting for the data, [6] tiles that walked
+__device__ unsigned long long g_tile_stats[8];
+#endif
+
 // Shared-memory scratch of the multi-split.
 struct SplitSmem {
   uint32_t* hist;  // [kTileWarps][kRadix] warp-private digit counters
@@ -155,6 +163,10 @@ __device__ __forceinline__ void split_tile(const uint32_t (&dig)[kTileItems], co
 
   // ---- exclusive prefix of this bin over all earlier tiles of the column (decoupled look-back) ----
   {
+#ifdef PBL_TILE_STATS
+    const long long lb_t0 = clock64();
+    unsigned long long lb_steps = 0;
+#endif
     uint32_t excl = 0;
     if (tile != 0) {
       constexpr int LB = 4;
@@ -179,11 +191,22 @@ __device__ __forceinline__ void split_tile(const uint32_t (&dig)[kTileItems], co
             }
             excl += (uint32_t)w;
             --t;
+#ifdef PBL_TILE_STATS
+            ++lb_steps;
+#endif
             if (w & kStatusInclusive) done = true;
           }
         }
       }
       st_relaxed_u64(&st[(size_t)tile * kRadix + tid], tag | kStatusInclusive | (uint32_t)(excl + cnt));
+#ifdef PBL_TILE_STATS
+      if (tid == 0) {
+        atomicAdd(&g_tile_stats[6], 1ull);
+        atomicAdd(&g_tile_stats[1], lb_steps);
+        atomicAdd(&g_tile_stats[2], (unsigned long long)spins);
+        atomicAdd(&g_tile_stats[3], (unsigned long long)(clock64() - lb_t0));
+      }
+#endif
     }
     sm.goff[tid] = bin_base + excl - bin_start;  // + position in tile order = global slot
   }
