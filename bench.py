@@ -3,6 +3,7 @@
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --gpus N --scaling strong  # N=1e8 rows in total, 1e8 / N per GPU
     python bench.py --impl reference          # the reference's CPU path (oracle port) on the host
 
 A step = one ImanConover.__call__-equivalent over one (N, d) batch of synthetic input:
@@ -32,10 +33,11 @@ IC_BYTES_PER_SAMPLE_VAR = 456.0  # fixed algorithmic acc
 # one digit pass moves 12 B in + 12 B out per key (u64 key + u32 row); the first of the 4 passes of the
 # 32-bit window reads the 8 B double instead of 12 B
 PASS_BYTES_PER_KEY = (3 * 24.0 + 20.0) / 4.0
-# measured DRAM traffic of one digit pass, dram__bytes_read.sum + dram__bytes_write.sum per key from the
-# `ncu --set full` capture profiles/r1_ncu_sort_kernels_summary.txt (3.2e8 keys per launch: 7.44 GB for
-# the pass that reads the raw doubles, 8.74 GB for each of the other three -> 26.3 B/key on average)
-PASS_DRAM_BYTES_PER_KEY_NCU = 26.3
+# measured DRAM traffic of one digit pass, dram__bytes_read.sum + dram__bytes_write.sum per key, from the
+# `ncu --set full` capture of the bench-size launches (N=1e8 x 16 = 1.6e9 keys per launch; raw CSV and
+# summary: profiles/r2_ncu_n1e8_*): see PASS_DRAM_BYTES_NCU_SOURCE
+PASS_DRAM_BYTES_PER_KEY_NCU = 24.0
+PASS_DRAM_BYTES_NCU_SOURCE = "pending capture"
 
 
 def hbm_peak():
@@ -54,34 +56,64 @@ def target_matrix(d):
     return 0.9 * np.corrcoef(A, rowvar=False) + 0.1 * np.eye(d)
 
 
-def make_workload_device(n, d, seed, torch):
-    """(n, d) fp64, column-major on the device: marginals cycling norm(1,2) / triang(0.5) /
-    gamma(a=2) by column (config 3 of BASELINE.json), from pseudo-random uniforms."""
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    X = torch.empty((d, n), dtype=torch.float64, device="cuda")
+MARGINALS = ("norm(loc=1, scale=2)", "triang(c=0.5)", "gamma(a=2)")  # cycling by column
+
+
+def make_workload_device(n, d, seed, torch, skip=0, timings=None):
+    """(n, d) fp64, column-major on the device, BASELINE.json configs[2] as SURVEY.md section 8(d) C3 states
+    it: scrambled Sobol' quantiles (probabilit_b200.qmc.Sobol, bit-identical with SciPy's for the seed) pushed
+    through the marginals norm(1, 2) / triang(0.5) / gamma(a=2) cycling by column with the library's ppf
+    kernels (pbl_ppf_f64, in place).  `skip`: rows of the sequence to skip (rank r of a multi-GPU run takes
+    rows [r*n, (r+1)*n)).  `timings`: dict that receives the device times of the two kernels."""
+    import warnings
+
+    from probabilit_b200 import _lib, qmc
+
+    lib = _lib.require_gpu()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    eng = qmc.Sobol(d, seed=seed, scramble=True)
+    eng.fast_forward(skip)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "balance properties of Sobol' points require n to be a power of 2"
+        X = eng.random(n, device=True)  # (n, d) view with strides (1, n)
+    e1.record()
+    # 30-bit Sobol' points are multiples of 2^-30 and a scrambled point can be exactly 0 (once in 1.6e9 values
+    # for this seed); norm.ppf(0) = -inf would leave the column with an infinite value, so such a point is
+    # moved to 2^-31 (a user of Node.sample has to do the same to keep the model finite)
+    X.clamp_(min=2.0 ** -31)
+    e1b = torch.cuda.Event(enable_timing=True)
+    e1b.record()
+    PPF = {0: (16, 1.0, 2.0, 0.0), 1: (19, 0.5, 0.0, 1.0), 2: (20, 2.0, 0.0, 1.0)}  # PBL_PPF_NORM / TRIANG / GAMMA
     for c in range(d):
-        u = torch.rand(n, generator=g, dtype=torch.float64, device="cuda")
-        u.clamp_(1e-300, 1 - 1e-16)
-        if c % 3 == 0:
-            X[c] = 1.0 + 2.0 * torch.special.ndtri(u)
-        elif c % 3 == 1:
-            X[c] = torch.where(u < 0.5, torch.sqrt(0.5 * u), 1.0 - torch.sqrt(0.5 * (1.0 - u)))
-        else:
-            u2 = torch.rand(n, generator=g, dtype=torch.float64, device="cuda").clamp_(1e-300, 1.0)
-            X[c] = -torch.log(u) - torch.log(u2)  # gamma(a=2) as a sum of two exponentials
-            del u2
-        del u
-    return X.T  # (n, d) view with strides (1, n)
+        what, p0, p1, p2 = PPF[c % 3]
+        ptr = C.c_void_p(X.data_ptr() + c * n * 8)
+        _lib.check(lib.pbl_ppf_f64(what, ptr, n, p0, p1, p2, ptr, stream), "pbl_ppf_f64")
+    e2.record()
+    torch.cuda.synchronize()
+    if timings is not None:
+        t_gen, t_ppf = e0.elapsed_time(e1) * 1e-3, e1b.elapsed_time(e2) * 1e-3
+        timings.update({
+            "sobol": {"ms": t_gen * 1e3, "samples_vars_per_s": n * d / t_gen, "bytes_per_sample_var": 8,
+                      "GB_per_s": 8.0 * n * d / t_gen / 1e9},
+            "ppf": {"ms": t_ppf * 1e3, "samples_vars_per_s": n * d / t_ppf, "bytes_per_sample_var": 16,
+                    "GB_per_s": 16.0 * n * d / t_ppf / 1e9, "marginals": list(MARGINALS)}})
+    return X
 
 
 def make_workload_host(n, d, seed):
-    """Same marginals on the host (NumPy/SciPy), for the CPU arm."""
+    """The same workload from the reference stack on the host (scipy.stats.qmc.Sobol + scipy ppfs)."""
+    import warnings
+
     import scipy.stats as st
 
-    rng = np.random.default_rng(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q = st.qmc.Sobol(d, seed=seed, scramble=True).random(n)
     X = np.empty((n, d), order="F")
     for c in range(d):
-        u = rng.random(n)
+        u = q[:, c]
         if c % 3 == 0:
             X[:, c] = st.norm(loc=1, scale=2).ppf(u)
         elif c % 3 == 1:
@@ -195,10 +227,15 @@ def time_graph(n, lib):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n_ref, d = args.ref_rows, args.d
+    d = args.d
+    n_ref = args.ref_rows
+    if n_ref <= 0:
+        # as many rows per step as keep the whole --steps/--warmup run within ~4 minutes (the CPU path
+        # takes ~5.5 us per row at d=16 around 1e6-1e7 rows), at most 1e7 (15 GB of host RAM)
+        n_ref = int(min(1e7, max(2e5, 240.0 / ((args.steps + args.warmup) * 5.5e-6))))
     from oracle import iman_conover as oic
 
-    X = make_workload_host(n_ref, d, seed=1)
+    X = make_workload_host(n_ref, d, seed=0)
     Ct = target_matrix(d)
     for _ in range(args.warmup):
         oic.iman_conover(X, Ct)
@@ -215,7 +252,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"Iman-Conover fp64 N={args.n} rows per GPU, d={d}, mixed norm/triang/gamma "
-                               "marginals (BASELINE.json configs[2]), pseudo-random uniforms",
+                               "marginals on scrambled Sobol' quantiles (BASELINE.json configs[2])",
                    "rows_per_gpu": args.n, "d": d, "cpu_rows_per_step": n_ref,
                    "note": "the reference's NumPy/SciPy path (oracle port) on the host cores; each step is a "
                            "bounded row sample of the workload"},
@@ -225,6 +262,50 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def multi_gpu_parity_check(n_small, d, Ct, rank, world, local_rank, dist, torch, lib):
+    """G-GPU == 1-GPU, bit for bit, before anything is timed (the driver's pytest box has one GPU, so this
+    is where the multi-GPU path is checked at round end): the same workload at n_small rows per GPU through
+    DistributedImanConover, gathered on rank 0 and compared with the single-plan result of the whole matrix."""
+    from probabilit_b200 import _lib
+    from probabilit_b200.correlation import _IcPlan
+    from probabilit_b200.distributed import DistributedImanConover
+
+    Xs = make_workload_device(n_small, d, seed=0, torch=torch, skip=rank * n_small)
+    Ys = torch.empty_strided(Xs.shape, Xs.stride(), dtype=Xs.dtype, device=Xs.device)
+    small = DistributedImanConover(n_small, d, Ct, dist)
+    small.run(Xs, Ys)
+    small.close()
+    # shards as [d][n_small] blocks; rank 0 stitches the (world * n_small, d) matrices together column-major
+    xs = [torch.empty((d, n_small), dtype=torch.float64, device="cuda") for _ in range(world)]
+    ys = [torch.empty((d, n_small), dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(xs, Xs.T.contiguous())
+    dist.all_gather(ys, Ys.T.contiguous())
+    verdict = torch.zeros(2, dtype=torch.int64, device="cuda")
+    if rank == 0:
+        nt = n_small * world
+        Xf = torch.cat(xs, dim=1).contiguous()  # [d][nt]
+        Yf = torch.empty_like(Xf)
+        plan = _IcPlan(nt, d, local_rank)
+        plan.set_target(np.linalg.cholesky(Ct))
+        st = lib.pbl_ic_plan_run(plan.handle, Xf.data_ptr(), 1, nt, Yf.data_ptr(), 1, nt,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        plan.close()
+        if st != 0:
+            raise RuntimeError(f"parity check: pbl_ic_plan_run status {st}: {_lib.last_error()}")
+        got = torch.cat(ys, dim=1)
+        verdict[0] = int(torch.equal(got, Yf))
+        verdict[1] = int((got != Yf).sum().item())
+        del Xf, Yf, got
+    dist.broadcast(verdict, 0)
+    del xs, ys, Xs, Ys
+    torch.cuda.empty_cache()
+    if not int(verdict[0].item()):
+        raise RuntimeError(f"bench: the {world}-GPU result differs from the single-GPU result in "
+                           f"{int(verdict[1].item())} entries")
+    return {"what": f"{world}-GPU DistributedImanConover == single-GPU plan, bit for bit",
+            "rows_per_gpu": n_small, "rows_total": n_small * world, "d": d, "equal": True}
 
 
 # ------------------------------------------------------------------------------------------
@@ -241,12 +322,20 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n, d = args.n, args.d
+    d = args.d
+    n = args.n // world if args.scaling == "strong" else args.n  # rows on this GPU
     Ct = target_matrix(d)
-    X = make_workload_device(n, d, seed=1234 + rank, torch=torch)
-    Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
+
+    parity = None
+    if world > 1 and args.parity_rows > 0:
+        parity = multi_gpu_parity_check(args.parity_rows, d, Ct, rank, world, local_rank, dist, torch, lib)
+
+    gen = {}
+    # one Sobol' sequence for the whole job: rank r holds its rows [r*n, (r+1)*n)
+    X = make_workload_device(n, d, seed=0, torch=torch, skip=rank * n, timings=gen)
+    Y = torch.empty_strided(X.shape, X.stride(), dtype=X.dtype, device=X.device)
 
     if world > 1:
         from probabilit_b200.distributed import DistributedImanConover
@@ -343,13 +432,13 @@ def run_ours(args, rank, world, local_rank):
                 lib.pbl_host_free_pinned(h)
         e2e = {"value": None, "unit": UNIT, "note": "pinned host buffers could not be allocated on every rank"}
     if world > 1 and args.e2e_steps > 0 and ok:
+        Xh = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(d, n)).T
+        Yh = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_double)), shape=(d, n)).T
         _lib.check(lib.pbl_memcpy_d2h(hx, C.c_void_p(X.data_ptr()), nbytes, sp))
         torch.cuda.synchronize()
 
         def e2e_step():
-            _lib.check(lib.pbl_memcpy_h2d(C.c_void_p(X.data_ptr()), hx, nbytes, sp))
-            runner.run(X, Y)
-            _lib.check(lib.pbl_memcpy_d2h(hy, C.c_void_p(Y.data_ptr()), nbytes, sp))
+            runner.run_host(Xh, Yh)  # H2D / D2H per exchange round, overlapped with the sorts
             torch.cuda.synchronize()
 
         e2e_step()
@@ -361,11 +450,14 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        if not np.array_equal(Xh[:1000, 0], Yh[:1000, 0]):
+            raise RuntimeError("bench e2e: column 0 changed")
         e2e = {"value": float(n) * d * world * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "api": "probabilit_b200.distributed.DistributedImanConover.run on row shards copied from / to "
-                      "pinned host memory (one PCIe link per GPU, copies not overlapped with the transform)"}
+               "api": "probabilit_b200.distributed.DistributedImanConover.run_host: every rank's row shard starts "
+                      "and ends in pinned host memory (one PCIe link per GPU); the copies go column by column, "
+                      "overlapped with the exchange rounds and the sorts"}
         lib.pbl_host_free_pinned(hx)
         lib.pbl_host_free_pinned(hy)
 
@@ -381,12 +473,12 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = hbm_peak()
     pass_gbs = PASS_BYTES_PER_KEY * nkeys.value / (pms.value * 1e-3) / 1e9 if pms.value > 0 else None
     roofline = {
-        "kernel": "onesweep_pass_kernel (one radix digit pass over all columns)",
+        "kernel": "pass_tma_kernel (one onesweep radix digit pass over all columns of a batch; persistent, "
+                  "cp.async.bulk + mbarrier double-buffered tiles)",
         "bound": "hbm", "achieved": pass_gbs, "peak": peak, "unit": "GB/s",
         "frac": (pass_gbs / peak) if pass_gbs else None,
         "traffic": PASS_DRAM_BYTES_PER_KEY_NCU * nkeys.value / max(nl.value, 1),
-        "traffic_source": "ncu --set full capture at n=2e7 (profiles/r1_ncu_sort_kernels_summary.txt), "
-                          "26.3 B/key (mean of the 4 passes) scaled to this launch's keys",
+        "traffic_source": PASS_DRAM_BYTES_NCU_SOURCE,
         "peak_source": peak_src,
         "launches_timed": nl.value, "avg_launch_ms": (pms.value / nl.value) if nl.value else None,
         "algorithmic_bytes_per_launch": PASS_BYTES_PER_KEY * nkeys.value / max(nl.value, 1),
@@ -405,15 +497,18 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Iman-Conover fp64 N={n} rows per GPU, d={d}, mixed norm/triang/gamma "
-                               "marginals (BASELINE.json configs[2]), pseudo-random uniforms",
-                   "rows_per_gpu": n, "d": d, "l2": "inputs (12.8 GB) far exceed the 126 MB L2",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Iman-Conover fp64 N={n} rows per GPU ({n * world} in total), d={d}, marginals "
+                               "norm(1,2) / triang(0.5) / gamma(2) cycling by column on scrambled Sobol' "
+                               "quantiles (seed 0), generated on the device by the library's own Sobol' and "
+                               "ppf kernels (BASELINE.json configs[2], SURVEY.md 8d C3)",
+                   "rows_per_gpu": n, "rows_total": n * world, "d": d,
+                   "l2": f"inputs ({n * d * 8 / 1e9:.1f} GB per GPU) far exceed the 126 MB L2",
                    "col_batch": args.col_batch,
                    **({"transport": "row <-> column transposes by copy engines over CUDA-IPC peer mappings "
                                     "(NVLink), NCCL for the Gram all-reduce and the barriers"} if world > 1 else {})},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "graph": graph,
+        "clocks": clocks, "generator": gen, "parity_check": parity, "graph": graph,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -431,7 +526,12 @@ def main():
     ap.add_argument("--col-batch", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=lambda s: int(float(s)), default=3_000_000)
-    ap.add_argument("--ref-rows", type=lambda s: int(float(s)), default=1_000_000)
+    ap.add_argument("--ref-rows", type=lambda s: int(float(s)), default=0,
+                    help="rows per step of the reference arm (0: sized to the --steps/--warmup budget)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows per GPU; strong: --rows in total, split over the GPUs")
+    ap.add_argument("--parity-rows", type=lambda s: int(float(s)), default=1_000_000,
+                    help="rows per GPU of the multi-GPU == single-GPU check that precedes the timing (0: skip)")
     ap.add_argument("--graph-rows", type=lambda s: int(float(s)), default=100_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

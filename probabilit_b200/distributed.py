@@ -247,12 +247,14 @@ class CudaPeerTransport:
             _lib.check(self.lib.pbl_peer_copy_many(n, dst, src, nb, C.c_void_p(self.side.cuda_stream)),
                        "pbl_peer_copy_many")
 
-    def push(self, copies, after, barrier=True):
-        """After `after` (a compute-stream event): copy, then (optionally) barrier.  Returns the event that
-        says "every rank's copies of this call have landed"."""
+    def push(self, copies, after, barrier=True, also_after=()):
+        """After `after` (a compute-stream event) and the events in `also_after`: copy, then (optionally)
+        barrier.  Returns the event that says "every rank's copies of this call have landed"."""
         torch = self.torch
         with torch.cuda.stream(self.side):
             self.side.wait_event(after)
+            for ev in also_after:
+                self.side.wait_event(ev)
             self._copies(copies)
             if barrier:
                 self.barrier()
@@ -311,6 +313,8 @@ class DistributedImanConover:
                 and os.environ.get("PBL_DIST_EXCHANGE", "peer") == "peer":
             transport = CudaPeerTransport(stages, dist)
         self.tp = transport  # None: torch.distributed send/recv rounds
+        self._x_ready = self._y_done = None
+        self._host = None  # device staging + copy stream of run_host
         self.trace = None  # developer aid (tools/dist_trace.py): list of (label, CUDA event) when enabled
 
     def _mark(self, label):
@@ -446,6 +450,60 @@ class DistributedImanConover:
         self._finish(status)
         return Y_local
 
+    # ------------------------------------------------------------------ host buffers
+    def run_host(self, X_host, Y_host):
+        """The same call with this rank's row shard in HOST memory (column-major (n_local, K) NumPy arrays,
+        ideally page-locked): the host->device copy of the columns of round r+1 overlaps the exchange and the
+        sorts of round r, and the columns of Y go back to the host round by round while the later rounds are
+        still being ranked -- the pipelining the single-GPU host entry point does (pbl_iman_conover_host_f64),
+        applied per exchange round.  Needs the peer-copy transport."""
+        if self.tp is None:
+            raise NotImplementedError("run_host needs the peer-copy transport (PBL_DIST_EXCHANGE=peer)")
+        torch_mod = self.st.torch
+        lib = self.st.lib
+        nl, k = self.n_local, self.k
+        for a in (X_host, Y_host):
+            if a.shape != (nl, k) or a.dtype != np.float64 or not (a.flags.f_contiguous or k == 1):
+                raise ValueError("run_host: (n_local, K) float64 column-major arrays expected")
+        if self._host is None:
+            dev = torch_mod.device("cuda", torch_mod.cuda.current_device())
+            self._host = {"x": torch_mod.empty((k, nl), dtype=torch_mod.float64, device=dev),
+                          "y": torch_mod.empty((k, nl), dtype=torch_mod.float64, device=dev),
+                          "copy": torch_mod.cuda.Stream()}
+        h = self._host
+        copy = h["copy"]
+        cs = C.c_void_p(copy.cuda_stream)
+        me = self.rank
+        ring = [(me + 1 + i) % self.world for i in range(self.world)]
+        cols_of_round = [[self.blocks[g][0] + r for g in ring if r < self.blocks[g][1] - self.blocks[g][0]]
+                         for r in range(self.rounds)]
+        # all H2D copies are queued at once, in the order the rounds need them; the copy stream first waits for
+        # whatever the caller queued on the compute stream (e.g. the previous call's last reads of the staging)
+        copy.wait_event(self.tp.compute_event())
+        ev_x = {}
+        for cols in cols_of_round:
+            for c in cols:
+                _lib.check(lib.pbl_memcpy_h2d(C.c_void_p(h["x"].data_ptr() + c * nl * 8),
+                                              C.c_void_p(X_host.ctypes.data + c * nl * 8), nl * 8, cs), "pbl_memcpy_h2d")
+                ev = torch_mod.cuda.Event()
+                ev.record(copy)
+                ev_x[c] = ev
+
+        def y_done(r, ev):
+            copy.wait_event(ev)
+            for c in cols_of_round[r]:
+                _lib.check(lib.pbl_memcpy_d2h(C.c_void_p(Y_host.ctypes.data + c * nl * 8),
+                                              C.c_void_p(h["y"].data_ptr() + c * nl * 8), nl * 8, cs), "pbl_memcpy_d2h")
+
+        self._x_ready = lambda r: [ev_x[c] for c in cols_of_round[r]]
+        self._y_done = y_done
+        try:
+            self._run_peer(h["x"], h["y"], None)
+        finally:
+            self._x_ready = self._y_done = None
+            copy.synchronize()
+        return Y_host
+
     # ------------------------------------------------------------------ the transform, peer copies
     def _run_peer(self, Xc, Yc, Y_local):
         """Same pipeline with the peer-copy transport.  Buffer hazards: a rank's buffers are only written by
@@ -464,18 +522,20 @@ class DistributedImanConover:
             return [((g, "x" if src is Xc else "scols", r * nt + me * nl), (None, src, (blocks[g][0] + r) * nl), nl)
                     for g in ring if r < blocks[g][1] - blocks[g][0]]
 
+        x_ready = self._x_ready or (lambda r: ())   # host staging (run_host): events of round r's source columns
+        y_done = self._y_done or (lambda r, ev: None)  # ... and "round r's columns of Y are complete"
         for _attempt in range(2):
             st.begin()
             self._mark("begin")
             # 1-3: X rows -> columns (push), rank + score each column, scores columns -> rows (push)
             # (the way back is sent row range by row range while the scatter that ends the stage is still
             # delivering the rest: chunk g = the rows of rank g, the ring successor first)
-            landed = tp.push(x_to_cols(0, Xc), tp.compute_event())
+            landed = tp.push(x_to_cols(0, Xc), tp.compute_event(), also_after=x_ready(0))
             for r in range(R):
                 tp.wait(landed)
                 self._mark(f"wait x{r}")
                 if r + 1 < R:
-                    landed = tp.push(x_to_cols(r + 1, Xc), tp.compute_event())
+                    landed = tp.push(x_to_cols(r + 1, Xc), tp.compute_event(), also_after=x_ready(r + 1))
                 if r < self.kc:
                     st.rank_scores(r, 1, first_chunk=ring[0], on_chunk=lambda g, r=r: tp.push(
                         [((g, "srows", (self.c0 + r) * nl), (me, "scols", r * nt + g * nl), nl)],
@@ -506,6 +566,7 @@ class DistributedImanConover:
                     self._mark(f"rank_gather {r}")
                 pulls.append(tp.pull([((None, Yc, (blocks[g][0] + r) * nl), (me, "srows", (blocks[g][0] + r) * nl), nl)
                                       for g in ring if r < blocks[g][1] - blocks[g][0]], tp.compute_event()))
+                y_done(r, pulls[-1])
             tp.wait(pulls[-1])
             self._mark("wait y back")
             status = self._agree(st.status())
@@ -529,6 +590,7 @@ class DistributedImanConover:
         return agreed - 10 if agreed >= 10 else agreed
 
     def close(self):
+        self._host = None
         if self.tp is not None:
             self.tp.close()
             self.tp = None

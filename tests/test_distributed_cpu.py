@@ -127,7 +127,7 @@ class SharedMemoryTransport:
     def compute_event(self):
         return None
 
-    def push(self, copies, after, barrier=True):
+    def push(self, copies, after, barrier=True, also_after=()):
         self._copies(copies)
         if barrier:
             self.dist.barrier()
