@@ -36,8 +36,11 @@ PASS_BYTES_PER_KEY = (3 * 24.0 + 20.0) / 4.0
 # measured DRAM traffic of one digit pass, dram__bytes_read.sum + dram__bytes_write.sum per key, from the
 # `ncu --set full` capture of the bench-size launches (N=1e8 x 16 = 1.6e9 keys per launch; raw CSV and
 # summary: profiles/r2_ncu_n1e8_*): see PASS_DRAM_BYTES_NCU_SOURCE
-PASS_DRAM_BYTES_PER_KEY_NCU = 24.0
-PASS_DRAM_BYTES_NCU_SOURCE = "pending capture"
+PASS_DRAM_BYTES_PER_KEY_NCU = 23.7
+PASS_DRAM_BYTES_NCU_SOURCE = ("ncu --set full capture AT THE BENCH SIZE (N=1e8 x 16 = 1.6e9 keys per launch; "
+                              "profiles/r2_ncu_full_n1e8_summary.txt + _raw.csv): 13.10 GB read + 20.05 GB written by "
+                              "the pass that reads the raw doubles, 19.42 + 20.05 GB by each of the other three -> "
+                              "23.7 B/key on average (23 algorithmic), scaled to this launch's keys")
 
 
 def hbm_peak():
