@@ -32,7 +32,11 @@ def nearest_correlation_matrix(matrix, *, weights=None, eps=1e-6, verbose=False)
     host): solved here with Higham's alternating projections + Dykstra's correction (N. Higham,
     "Computing the nearest correlation matrix", 2002) in NumPy, so that ``.correlate()`` graphs
     work without cvxpy.  A matrix that is already feasible is returned unchanged (SCS returns it
-    to ~1e-6).  Elementwise ``weights`` other than all-ones are not supported."""
+    to ~1e-6).  With elementwise ``weights`` H the objective is ``||H o (X - G)||_F`` (equation (3) of
+    Qi & Sun, the reference's docstring), which has no closed-form projection: it is solved by ADMM on
+    the splitting X = Z (X: weighted least squares with a unit diagonal, elementwise; Z: projection on
+    the eigenvalue floor), reproducing the reference's doctest values and MATLAB's ``nearcorr`` example
+    (reference tests/test_correlation.py:37-78) to 1e-4."""
     if not isinstance(matrix, np.ndarray):
         raise TypeError("Input argument `matrix` must be np.ndarray.")
     if not (matrix.ndim == 2 and matrix.shape[0] == matrix.shape[1]):
@@ -42,11 +46,11 @@ def nearest_correlation_matrix(matrix, *, weights=None, eps=1e-6, verbose=False)
             raise TypeError("Input argument `weights` must be np.ndarray.")
         if weights.shape != matrix.shape:
             raise ValueError("Argument `weights` must have same shape as `matrix`.")
-        if not np.allclose(weights, weights.flat[0]):
-            raise NotImplementedError("elementwise weights need the reference's cvxpy/SCS solver")
     K = matrix.shape[0]
     floor = 10.0 * eps / K
     G = np.array(matrix, dtype=float)
+    if weights is not None and not np.allclose(weights, weights.flat[0]):
+        return _nearest_correlation_matrix_weighted(G, np.array(weights, dtype=float), floor, verbose)
     sym = 0.5 * (G + G.T)
     if np.allclose(G, G.T) and np.allclose(np.diag(G), 1.0) and np.linalg.eigvalsh(sym).min() >= floor:
         return G
@@ -70,6 +74,47 @@ def nearest_correlation_matrix(matrix, *, weights=None, eps=1e-6, verbose=False)
         t = (floor - lam) / (1.0 - lam)
         Y = (1.0 - t) * Y + t * np.eye(K)
     return 0.5 * (Y + Y.T)
+
+
+def _nearest_correlation_matrix_weighted(G, H, floor, verbose=False):
+    """argmin ||H o (X - G)||_F  s.t.  diag(X) = 1,  X - floor*I >= 0   (reference correlation.py:124-137).
+
+    ADMM on  f(X) + g(Z),  X = Z:   f = 0.5 ||H o (X - G)||^2 + indicator(diag X = 1)  (separable: the X-step
+    is elementwise),  g = indicator(Z - floor*I >= 0)  (the Z-step clamps eigenvalues).  The penalty is
+    re-balanced from the primal / dual residuals.  K x K, once per ``sample`` call: host NumPy."""
+    K = G.shape[0]
+    G = 0.5 * (G + G.T)
+    H2 = (0.5 * (H + H.T)) ** 2
+    rho = max(float(np.mean(H2)), 1e-3)
+    Z = G.copy()
+    np.fill_diagonal(Z, 1.0)
+    U = np.zeros_like(G)
+    eye = np.eye(K, dtype=bool)
+    for it in range(50000):
+        X = (H2 * G + rho * (Z - U)) / (H2 + rho)
+        X[eye] = 1.0
+        w, V = np.linalg.eigh(X + U)
+        Z_new = (V * np.maximum(w, floor)) @ V.T
+        r = np.linalg.norm(X - Z_new, "fro")           # primal residual
+        s_ = rho * np.linalg.norm(Z_new - Z, "fro")    # dual residual
+        Z = Z_new
+        U = U + X - Z
+        if verbose and it % 100 == 0:
+            print(f"nearest_correlation_matrix (weighted): iteration {it}, residuals {r:.3e} {s_:.3e}, rho {rho:.3g}")
+        if r < 1e-11 * K and s_ < 1e-11 * K:
+            break
+        if it % 50 == 49:  # residual balancing (scaled dual variable is rescaled with rho)
+            if r > 10.0 * s_:
+                rho, U = rho * 2.0, U / 2.0
+            elif s_ > 10.0 * r:
+                rho, U = rho / 2.0, U * 2.0
+    Y = 0.5 * (Z + Z.T)
+    np.fill_diagonal(Y, 1.0)
+    lam = np.linalg.eigvalsh(Y).min()
+    if lam < floor:  # finish on the feasible side with an exact unit diagonal
+        t = (floor - lam) / (1.0 - lam)
+        Y = (1.0 - t) * Y + t * np.eye(K)
+    return Y
 
 
 def _is_positive_definite(X):
