@@ -7,6 +7,8 @@
 //   method "lhs"     scipy.stats.qmc.LatinHypercube        -> lhs_kernel            (statistical parity)
 // Every point is a pure function of its row index, so row shards on several GPUs need no
 // communication (skip-ahead = start the index at the shard's first row).
+#include <type_traits>
+
 #include "../../include/probabilit_b200.h"
 #include "common.cuh"
 #include "philox.cuh"
@@ -89,39 +91,56 @@ __global__ void sobol_scramble_kernel(const uint8_t* __restrict__ ltm_bits, cons
   }
 }
 
-// point j = (shift ^ XOR_{b set in gray(j)} sv[b]) * 2^-bits; rows (j, j+1) with j even share all
-// but sv[0].  One thread: two consecutive rows of one dimension.
+// point j = (shift ^ XOR_{b set in gray(j)} sv[b]) * 2^-bits.  One thread: the 8 consecutive points of an
+// aligned group j0 = 8 g .. 8 g + 7 of one dimension.  gray(j0 + t) = gray(j0) ^ gray(t) for t < 8 (j0 has
+// its three low bits clear), so the group shares B = shift ^ XOR_{b in gray(j0)} sv[b] -- one walk over the
+// set bits per 8 points instead of per point -- and point t is B ^ C[t] with the 8 combinations C[t] of
+// sv[0..2] staged once per block.  64 contiguous bytes per thread go out as four 128-bit stores.
+// NARROW: bits <= 32, the whole computation in 32-bit registers.
+template <bool NARROW>
 __global__ void __launch_bounds__(256)
 sobol_points_kernel(const uint64_t* __restrict__ sv, const uint64_t* __restrict__ shift, int32_t bits,
                     uint64_t skip, int64_t n, double* __restrict__ out, int64_t row_stride,
                     int64_t col_stride) {
-  __shared__ uint64_t s_sv[64];
+  using W = typename std::conditional<NARROW, uint32_t, uint64_t>::type;
+  __shared__ W s_sv[64];
+  __shared__ W s_c[8];
   const int c = blockIdx.y;
-  if (threadIdx.x < bits) s_sv[threadIdx.x] = sv[(size_t)c * bits + threadIdx.x];
+  if (threadIdx.x < 64) s_sv[threadIdx.x] = threadIdx.x < bits ? (W)sv[(size_t)c * bits + threadIdx.x] : (W)0;
   __syncthreads();
-  // pairs are aligned to even *global* indices; the first/last pair of a shard may be half used
-  const uint64_t first_pair = skip >> 1;
-  const uint64_t pair = first_pair + (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  const uint64_t j0 = pair << 1;
+  if (threadIdx.x < 8) {
+    const uint32_t g = threadIdx.x ^ (threadIdx.x >> 1);
+    s_c[threadIdx.x] = ((g & 1u) ? s_sv[0] : (W)0) ^ ((g & 2u) ? s_sv[1] : (W)0) ^ ((g & 4u) ? s_sv[2] : (W)0);
+  }
+  __syncthreads();
+  // groups are aligned to multiples of 8 of the GLOBAL index; the first / last group of a shard may be partial
+  const uint64_t group = (skip >> 3) + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint64_t j0 = group << 3;
   if (j0 >= skip + (uint64_t)n) return;
   uint64_t g = j0 ^ (j0 >> 1);
-  uint64_t q = shift[c];
+  W base = (W)shift[c];
   while (g) {
-    int b = __ffsll((long long)g) - 1;
-    q ^= s_sv[b];
+    const int b = __ffsll((long long)g) - 1;
+    base ^= s_sv[b];
     g &= g - 1;
   }
   const double scale = __longlong_as_double((long long)(1023 - bits) << 52);  // 2^-bits
-  const double a = __ull2double_rn(q) * scale;
-  const double b = __ull2double_rn(q ^ s_sv[0]) * scale;
-  const int64_t r0 = (int64_t)(j0 - skip);  // may be -1 for the first pair
+  double v[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const W q = base ^ s_c[t];
+    v[t] = (NARROW ? __uint2double_rn((uint32_t)q) : __ull2double_rn((uint64_t)q)) * scale;
+  }
+  const int64_t r0 = (int64_t)(j0 - skip);  // negative for the head of a partial first group
   double* colp = out + (int64_t)c * col_stride;
-  if (r0 >= 0 && r0 + 1 < n && row_stride == 1 &&
-      ((reinterpret_cast<uintptr_t>(colp + r0) & 15) == 0)) {
-    *reinterpret_cast<double2*>(colp + r0) = make_double2(a, b);
+  if (r0 >= 0 && r0 + 8 <= n && row_stride == 1 && ((reinterpret_cast<uintptr_t>(colp + r0) & 15) == 0)) {
+    double2* p = reinterpret_cast<double2*>(colp + r0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) p[t] = make_double2(v[2 * t], v[2 * t + 1]);
   } else {
-    if (r0 >= 0) colp[r0 * row_stride] = a;
-    if (r0 + 1 < n) colp[(r0 + 1) * row_stride] = b;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (r0 + t >= 0 && r0 + t < n) colp[(r0 + t) * row_stride] = v[t];
   }
 }
 
@@ -259,10 +278,14 @@ int pbl_sobol_f64(const uint64_t* sv_dev, const uint64_t* shift_dev, int32_t d, 
                   void* stream) {
   if (d < 0 || n < 0 || bits < 1 || bits > 64 || !sv_dev || !shift_dev || !out_dev) return kBadShape;
   if (n == 0 || d == 0) return kOk;
-  const uint64_t npairs = ((skip + (uint64_t)n + 1) >> 1) - (skip >> 1);
-  dim3 grid((unsigned)((npairs + 255) / 256), (unsigned)d);
-  pbl::sobol_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sv_dev, shift_dev, bits, skip, n, out_dev,
-                                                                 row_stride, col_stride);
+  const uint64_t ngroups = ((skip + (uint64_t)n + 7) >> 3) - (skip >> 3);
+  dim3 grid((unsigned)((ngroups + 255) / 256), (unsigned)d);
+  if (bits <= 32)
+    pbl::sobol_points_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(sv_dev, shift_dev, bits, skip, n, out_dev,
+                                                                         row_stride, col_stride);
+  else
+    pbl::sobol_points_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(sv_dev, shift_dev, bits, skip, n, out_dev,
+                                                                          row_stride, col_stride);
   PBL_LAUNCH_CHECK();
   return kOk;
 }

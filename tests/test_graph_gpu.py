@@ -147,11 +147,20 @@ def test_gamma_ulp_distribution():
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/gamma_ppf_ulp.json", "w") as f:
         json.dump(report, f, indent=1)
-    # scipy's gammaincinv is itself 5-145 ulp from the truth depending on a (tools/gamma_truth.py, mpmath;
-    # profiles/r1_gamma_truth.json): "4 ulp of scipy" holds for the bulk only where scipy is accurate
-    for a in ("1.0", "2.0", "9.0"):
-        assert report[a]["frac_le_4"] > 0.98, report[a]
-    assert report["2.5"]["frac_le_4"] > 0.85 and report["2.5"]["max"] <= 64, report["2.5"]
+    # The device restates SciPy's own algorithm (Cephes / xsf igami: DiDonato-Morris start, exactly three
+    # Halley steps, no FMA contraction), so the bar of 4 ulp of SciPy holds for the bulk wherever the
+    # problem does not amplify the last-place differences between CUDA's and glibc's log / exp / lgamma:
+    for a in ("1.0", "2.0", "2.5", "9.0", "30.0", "1000.0"):
+        assert report[a]["frac_le_4"] > 0.98, (a, report[a])
+    # a < 1: P(a, x) ~ x^a / Gamma(a+1), so dx/x = (1/a) dP/P, and P itself comes from
+    # exp(a log x - x - lgamma a), whose argument carries ~1e-16 ABSOLUTE error from each libm call: two
+    # implementations scatter by 2-3 ulp in P and 1/a times that in x whatever the algorithm.  SciPy is itself
+    # 2.4 ulp (a = 0.5) / 34 ulp (a = 0.05) in the median from the mpmath truth, the device 2.4 / 19
+    # (tools/gamma_truth.py -> profiles/r2_gamma_truth.json).  a = 150: the same through x^a (a ulp of log x is
+    # a ulp of the result).  Those shapes are bounded, not held to 4 ulp:
+    assert report["0.5"]["frac_le_4"] > 0.7 and report["0.5"]["p99"] <= 128, report["0.5"]
+    assert report["0.05"]["p99"] < 400, report["0.05"]
+    assert report["150.0"]["frac_le_4"] > 0.9 and report["150.0"]["max"] <= 32, report["150.0"]
 
 
 @pytest.mark.parametrize("name", list(graph_recipes.RECIPES))

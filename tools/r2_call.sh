@@ -1,5 +1,9 @@
 set -u
-for tag in base STG SC W4 W8 ALL; do
-  lib=$PWD/tools/micro/lib_$tag.so; [ $tag = base ] && lib=$PWD/probabilit_b200/libprobabilit_b200.so
-  echo "$tag: $(PBL_LIB=$lib timeout 300 python tools/stage_times.py 1e8 16 3 0 2>&1 | grep total_ms | tail -1)  single: $(PBL_LIB=$lib timeout 300 python tools/stage_times.py 1e8 4 3 1 2>&1 | grep total_ms | tail -1)"
-done
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_graph_gpu.py -x -q 2>&1 | tail -3
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/gamma_ppf_ulp.json'))
+for k,v in d.items(): print(k,v)
+PY
+timeout 300 python tools/graph_times.py 2>&1 | tail -5
