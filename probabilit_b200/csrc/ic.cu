@@ -804,11 +804,13 @@ chol_solve_kernel(const double* __restrict__ G, const double* __restrict__ colsu
 // The same computation for wide problems (k > 64), spread over the whole GPU with grid-wide barriers
 // (cooperative launch): the single-block version is bound by one SM's L2 bandwidth (k^3/3 updates
 // of an 8 MB matrix), this one by 3 grid barriers per column.
+constexpr int kCholPanel = 32;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 chol_solve_grid_kernel(const double* __restrict__ G, const double* __restrict__ colsum,
                        const double* __restrict__ P, double* __restrict__ W, double* __restrict__ T,
-                       int k, double n_total, uint32_t* __restrict__ flags, const double* __restrict__ colstd) {
+                       int k, double n_total, uint32_t* __restrict__ flags, const double* __restrict__ colstd,
+                       int rhs_warps) {
   cg::grid_group grid = cg::this_grid();
   const int nth = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, gwarp = gt >> 5, nwarps = nth >> 5;
@@ -829,38 +831,90 @@ chol_solve_grid_kernel(const double* __restrict__ G, const double* __restrict__ 
     }
     grid.sync();
   }
-  for (int j = 0; j < k; ++j) {
-    const double d = W[(size_t)j * k + j];  // identical in every thread: a consistent early exit
-    if (!(d > 0.0)) {
-      if (gt == 0) flags[kFlagNotPD] = 1u;
+  // Blocked right-looking Cholesky (lower triangle, in place), panels of kCholPanel columns: 3 grid barriers
+  // per PANEL instead of per column (the column-by-column form spent 3 k barriers of ~15 us: 58 ms at
+  // k = 1024).  (1) block 0 factors the diagonal block in shared memory, (2) every row below solves its
+  // slice of the panel against it, (3) the trailing lower triangle takes the rank-kCholPanel update.
+  constexpr int NB = kCholPanel;
+  __shared__ double sL[NB][NB + 1];
+  __shared__ int s_bad;
+  for (int j0 = 0; j0 < k; j0 += NB) {
+    const int nb = min(NB, k - j0);
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) s_bad = 0;
+      for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) sL[e / nb][e % nb] = W[(size_t)(j0 + e / nb) * k + j0 + e % nb];
+      __syncthreads();
+      for (int j = 0; j < nb; ++j) {
+        const double d = sL[j][j];
+        if (!(d > 0.0)) {  // same acceptance as LAPACK dpotrf: the pivot must be > 0 and not NaN
+          if (threadIdx.x == 0) s_bad = 1;
+          break;           // (d is the same in every thread of the block)
+        }
+        const double q = sqrt(d);
+        __syncthreads();
+        for (int i = j + 1 + (int)threadIdx.x; i < nb; i += blockDim.x) sL[i][j] /= q;
+        if (threadIdx.x == 0) sL[j][j] = q;
+        __syncthreads();
+        for (int e = threadIdx.x; e < (nb - j - 1) * (nb - j - 1); e += blockDim.x) {
+          const int i = j + 1 + e / (nb - j - 1), m = j + 1 + e % (nb - j - 1);
+          if (m <= i) sL[i][m] -= sL[i][j] * sL[m][j];
+        }
+        __syncthreads();
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nb * nb; e += blockDim.x)
+        if (e % nb <= e / nb) W[(size_t)(j0 + e / nb) * k + j0 + e % nb] = sL[e / nb][e % nb];
+      if (threadIdx.x == 0 && s_bad) flags[kFlagNotPD] = 1u;
+      __threadfence();
+    }
+    grid.sync();
+    if (*reinterpret_cast<volatile uint32_t*>(&flags[kFlagNotPD])) {  // the same verdict in every block
       for (int e = gt; e < k * k; e += nth) T[e] = 0.0;
       return;
     }
-    const double q = sqrt(d);
-    grid.sync();  // everybody has read the pivot
-    for (int i = j + 1 + gt; i < k; i += nth) W[(size_t)i * k + j] /= q;
-    if (gt == 0) W[(size_t)j * k + j] = q;
+    // (2) rows below the panel: W[i, j0 : j0+nb] <- W[i, j0 : j0+nb] L11^-T   (one thread per row)
+    for (int i = j0 + nb + gt; i < k; i += nth) {
+      double* wi = W + (size_t)i * k + j0;
+      for (int c = 0; c < nb; ++c) {
+        const double* lc = W + (size_t)(j0 + c) * k + j0;
+        double v = wi[c];
+        for (int m = 0; m < c; ++m) v -= wi[m] * lc[m];
+        wi[c] = v / lc[c];
+      }
+    }
     grid.sync();
-    for (int i = j + 1 + gwarp; i < k; i += nwarps) {
-      const double wij = W[(size_t)i * k + j];
-      for (int m = j + 1 + lane; m <= i; m += 32) W[(size_t)i * k + m] -= wij * W[(size_t)m * k + j];
+    // (3) trailing update of the lower triangle: one warp per row i, lanes along m
+    for (int i = j0 + nb + gwarp; i < k; i += nwarps) {
+      const double* wi = W + (size_t)i * k + j0;
+      for (int m = j0 + nb + lane; m <= i; m += 32) {
+        const double* wm = W + (size_t)m * k + j0;
+        double acc = 0.0;
+        for (int c = 0; c < nb; ++c) acc += wi[c] * wm[c];
+        W[(size_t)i * k + m] -= acc;
+      }
     }
     grid.sync();
   }
-  // T = Q^-T P^T by back substitution, one thread per column of T
-  for (int c = gt; c < k; c += nth) {
-    for (int i = k - 1; i >= 0; --i) {
-      if (i > c) {
-        T[(size_t)i * k + c] = 0.0;
-        continue;
+  // T = Q^-T P^T: column c of T solves Q^T t = P[c, :]^T (back substitution).  One WARP per column, in the
+  // column-oriented (axpy) form: once t_m is final, s_i -= Q[m][i] t_m for all i < m -- a coalesced read
+  // of row m of Q -- with the right-hand side in a shared-memory scratch of the warp.
+  extern __shared__ double s_rhs[];  // [warps_per_block_active][k]
+  const int warp_in_block = threadIdx.x >> 5;
+  if (warp_in_block < rhs_warps) {
+    double* sr = s_rhs + (size_t)warp_in_block * k;
+    const int active_warps = gridDim.x * rhs_warps;
+    for (int c = blockIdx.x * rhs_warps + warp_in_block; c < k; c += active_warps) {
+      for (int i = lane; i <= c; i += 32) sr[i] = P[(size_t)c * k + i];
+      for (int i = c + 1 + lane; i < k; i += 32) T[(size_t)i * k + c] = 0.0;
+      __syncwarp();
+      const double sd = MODE == 1 ? colstd[c] : 1.0;
+      for (int m = c; m >= 0; --m) {
+        const double* qm = W + (size_t)m * k;
+        const double t = sr[m] / qm[m];
+        for (int i = lane; i < m; i += 32) sr[i] -= qm[i] * t;
+        if (lane == 0) T[(size_t)m * k + c] = MODE == 1 ? t * sd : t;
+        __syncwarp();
       }
-      double s = P[(size_t)c * k + i];
-      for (int m = i + 1; m <= c; ++m) s -= W[(size_t)m * k + i] * T[(size_t)m * k + c];
-      T[(size_t)i * k + c] = s / W[(size_t)i * k + i];
-    }
-    if (MODE == 1) {
-      const double sd = colstd[c];
-      for (int i = 0; i <= c; ++i) T[(size_t)i * k + c] *= sd;
     }
   }
 }
@@ -880,11 +934,20 @@ int launch_chol_solve(IcPlan* p, double n_total, const double* colstd, cudaStrea
   double* W = p->work;
   double* T = p->T;
   uint32_t* fl = p->flags;
-  void* args[] = {&G, &cs, &P, &W, &T, &k, &n_total, &fl, &colstd};
+  // shared-memory scratch of the back substitution: one right-hand side (k doubles) per active warp
+  int rhs_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(96 * 1024) / ((size_t)k * 8)));
+  const size_t smem = (size_t)rhs_warps * k * 8;
+  static bool attr = false;
+  if (!attr) {
+    PBL_CUDA_CHECK(cudaFuncSetAttribute(chol_solve_grid_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        96 * 1024));
+    attr = true;
+  }
+  void* args[] = {&G, &cs, &P, &W, &T, &k, &n_total, &fl, &colstd, &rhs_warps};
   int per_sm = 0;
-  PBL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_solve_grid_kernel<MODE>, 256, 0));
+  PBL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_solve_grid_kernel<MODE>, 256, smem));
   const int blocks = std::max(1, std::min(per_sm, 2) * num_sms());
-  PBL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)chol_solve_grid_kernel<MODE>, dim3(blocks), dim3(256), args, 0,
+  PBL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)chol_solve_grid_kernel<MODE>, dim3(blocks), dim3(256), args, smem,
                                              stream));
   PBL_LAUNCH_CHECK();
   return kOk;
@@ -1052,6 +1115,8 @@ transform_tiled_kernel(double* __restrict__ S, int64_t n, int k, const double* _
   }
 }
 
+#include "fp64_tiles.cuh"
+
 template <typename T_>
 int dev_alloc(T_** p, size_t count, IcPlan* plan) {
   size_t bytes = std::max<size_t>(count * sizeof(T_), 16);
@@ -1060,7 +1125,9 @@ int dev_alloc(T_** p, size_t count, IcPlan* plan) {
   return kOk;
 }
 
-int gram_tg_for(int k) { return k <= 16 ? 4 : (k <= 32 ? 8 : 16); }
+// thread-grid edge of the Gram kernel: 4 / 8 / 16 (4 x 4 outputs per thread); 32 = the 128 x 128 tiles of
+// gram_big_kernel for wide problems (fp64_tiles.cuh)
+int gram_tg_for(int k) { return k <= 16 ? 4 : (k <= 32 ? 8 : (k <= 64 ? 16 : 32)); }
 
 }  // namespace
 
@@ -1132,7 +1199,20 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
   const int npairs = nt * (nt + 1) / 2;
   int64_t max_rb = (n + kGramSmallRows - 1) / kGramSmallRows;
   // whole waves: gram_small_kernel runs 3 blocks per SM, gram_kernel 4
-  int want = std::max(1, ((p->gram_tg == 4 ? 3 : 4) * num_sms() + npairs - 1) / npairs);
+  int want = std::max(1, ((p->gram_tg == 4 ? 3 : (p->gram_tg == 32 ? 1 : 4)) * num_sms() + npairs - 1) / npairs);
+  if (p->gram_tg == 32) {
+    // one 254-register block per SM: pick the row-block count whose grid fills whole waves best (36 tile
+    // pairs at k = 1024: 4 row blocks = 144 of 148 SMs in one wave, where 5 would run 1.2 waves)
+    double best_eff = 0.0;
+    for (int nrb = 1; nrb <= 16; ++nrb) {
+      const int blocks = npairs * nrb, waves = (blocks + num_sms() - 1) / num_sms();
+      const double eff = (double)blocks / ((double)waves * num_sms());
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        want = nrb;
+      }
+    }
+  }
   p->gram_row_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_rb, want));
   A(&p->gram_partials, (size_t)npairs * p->gram_row_blocks * (CT * CT + CT));
   if (rc != kOk) {
@@ -1210,7 +1290,8 @@ static int launch_post_tma(IcPlan* p, int c, int nb, int shift, uint32_t epoch, 
   a.epoch = epoch;
   a.col_base = c;
   a.part_shift = shift;
-  a.ncols_interleave = tickets_interleaved() ? (uint32_t)nb : 0u;
+  a.ncols = (uint32_t)nb;
+  a.ncols_interleave = tickets_interleaved() ? std::min<uint32_t>((uint32_t)nb, kInterleaveWidth) : 0u;
   PBL_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   const unsigned grid = (unsigned)std::min<size_t>((size_t)2 * num_sms(), (size_t)a.total_tiles);
   post_tma_kernel<MODE><<<grid, kTileThreads, kPostTmaSmemBytes, stream>>>(a);
@@ -1305,12 +1386,19 @@ int ic_stage_gram(IcPlan* p, cudaStream_t stream) {
   const int npairs = nt * (nt + 1) / 2;
   const int nrb = p->gram_row_blocks;
   int64_t rows_per = (p->n + nrb - 1) / nrb;
-  const int step_rows = TG == 4 ? kGramSmallRows : kGramRows;
+  const int step_rows = TG == 4 ? kGramSmallRows : (TG == 32 ? kBD : kGramRows);
   rows_per = (rows_per + step_rows - 1) / step_rows * step_rows;
   dim3 grid((unsigned)nrb, (unsigned)npairs);
   size_t smem = (size_t)2 * CT * (kGramRows + 1) * 8;
   smem = std::max(smem, (size_t)TG * TG * 20 * 8);
-  if (TG == 4)  // k <= 16: one tile pair
+  if (TG == 32) {  // wide: FP64-bound 128 x 128 tiles
+    static bool attr = false;
+    if (!attr) {
+      PBL_CUDA_CHECK(cudaFuncSetAttribute(gram_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramBigSmem));
+      attr = true;
+    }
+    gram_big_kernel<<<grid, 256, kGramBigSmem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
+  } else if (TG == 4)  // k <= 16: one tile pair
     gram_small_kernel<<<(unsigned)nrb, 256, 0, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
   else if (TG == 8)
     gram_kernel<8><<<grid, 256, smem, stream>>>(p->scores, p->n, p->k, p->gram_partials, nrb, rows_per);
@@ -1349,8 +1437,17 @@ int ic_stage_transform(IcPlan* p, cudaStream_t stream) {
     transform_small_kernel<16><<<blocks, 256, 0, stream>>>(p->scores, n, k, p->T);
   else if (k <= 32)
     transform_small_kernel<32><<<blocks, 256, 0, stream>>>(p->scores, n, k, p->T);
-  else
+  else if (k <= 64)
     transform_tiled_kernel<<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(p->scores, n, k, p->T);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      PBL_CUDA_CHECK(cudaFuncSetAttribute(transform_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kTransformBigSmem));
+      attr = true;
+    }
+    transform_big_kernel<<<(unsigned)((n + kBT - 1) / kBT), 256, kTransformBigSmem, stream>>>(p->scores, n, k, p->T);
+  }
   PBL_LAUNCH_CHECK();
   return kOk;
 }

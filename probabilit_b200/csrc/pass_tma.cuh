@@ -41,10 +41,8 @@ struct TmaArgs {
   uint32_t* ticket;         // one counter for the launch
   uint32_t total_tiles;     // ncols * ntiles
   uint32_t epoch;           // 1 .. 2^28, different for every launch that uses status64
-  // Ticket order.  ncols_interleave > 0: ticket g works on column g % ncols, tile g / ncols, so that the
-  // tiles in flight at any moment (2 per SM) are spread over all the columns of the batch and a tile's
-  // look-back finds an inclusive predecessor a few tiles back instead of a few hundred (the chained scan
-  // is per column).  0: column after column.
+  uint32_t ncols;
+  // Ticket order (ticket_to_tile): width of the column groups whose tiles are interleaved; 0: column after column.
   uint32_t ncols_interleave;
 };
 
@@ -64,13 +62,7 @@ __device__ __forceinline__ void tma_issue(const TmaArgs& a, uint32_t g, TmaTicke
       mbar_arrive(full);
       return;
     }
-    if (a.ncols_interleave) {
-      tk.tile = g / a.ncols_interleave;
-      tk.col = g - tk.tile * a.ncols_interleave;
-    } else {
-      tk.col = g / ntiles;
-      tk.tile = g - tk.col * ntiles;
-    }
+    ticket_to_tile(g, a.ncols, ntiles, a.ncols_interleave, &tk.col, &tk.tile);
     if (a.p.plan[tk.col].run[pass]) break;
     g = atomicAdd(a.ticket, 1u);  // constant digit: the column sits this pass out
   }

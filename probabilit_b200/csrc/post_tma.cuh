@@ -61,7 +61,8 @@ struct PostArgs {
   uint32_t epoch;
   int col_base;           // global index of the batch's first column
   int part_shift;         // row >> part_shift = row window; 32: no grouping (short columns)
-  uint32_t ncols_interleave;  // ticket order, as in the digit pass (pass_tma.cuh)
+  uint32_t ncols;
+  uint32_t ncols_interleave;  // ticket order: width of the interleaved column groups (ticket_to_tile)
 };
 
 struct PostSmem {
@@ -90,13 +91,7 @@ __device__ __forceinline__ void post_issue(const PostArgs& a, uint32_t g, PostTi
     mbar_arrive(full);
     return;
   }
-  if (a.ncols_interleave) {
-    tk.tile = g / a.ncols_interleave;
-    tk.col = g - tk.tile * a.ncols_interleave;
-  } else {
-    tk.col = g / a.ntiles;
-    tk.tile = g - tk.col * a.ntiles;
-  }
+  ticket_to_tile(g, a.ncols, a.ntiles, a.ncols_interleave, &tk.col, &tk.tile);
   tk.sh = a.maps[tk.col].sh;
   tk.pad[0] = tk.pad[1] = 0;
   const uint32_t tile_start = tk.tile * (uint32_t)kTile;

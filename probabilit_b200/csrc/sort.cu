@@ -803,7 +803,8 @@ int launch_pass_tma(const PassArgs& a, int ncols, const SortBuffers& buf, cudaSt
   t.status64 = reinterpret_cast<uint64_t*>(buf.status);
   t.ticket = a.tile_counter;
   t.total_tiles = (uint32_t)ncols * (uint32_t)a.ntiles;
-  t.ncols_interleave = tickets_interleaved() ? (uint32_t)ncols : 0u;
+  t.ncols = (uint32_t)ncols;
+  t.ncols_interleave = tickets_interleaved() ? std::min<uint32_t>((uint32_t)ncols, kInterleaveWidth) : 0u;
   PBL_RETURN_IF(next_epoch(buf, sort_status_bytes(ncols, a.n), stream, &t.epoch));
   const unsigned grid = (unsigned)std::min<size_t>((size_t)2 * num_sms(), (size_t)t.total_tiles);
   pass_tma_kernel<<<grid, kTileThreads, kTmaSmemBytes, stream>>>(t);

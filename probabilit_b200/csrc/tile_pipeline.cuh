@@ -77,6 +77,31 @@ __device__ __forceinline__ void st_u32_at(uint32_t* base, uint32_t idx, uint32_t
 __device__ unsigned long long g_tile_stats[8];
 #endif
 
+// Ticket -> (column, tile).  Tickets are handed out in GROUPS of `width` columns (the last group may be
+// narrower): inside a group ticket r works on column r % w, tile r / w, so that the tiles in flight at any
+// moment (2 per SM) are spread over the group's columns and a tile's look-back finds an inclusive
+// predecessor a few tiles back instead of a few hundred (the chained scan is per column).  The width is
+// capped (kInterleaveWidth): every column in flight keeps 256 partly written 128 B lines per output array in
+// L2, and with 1024 columns interleaved (d = 1024: 67 MB of write frontier) they were evicted half
+// written -- the passes ran at half speed.  width 0: column after column.
+constexpr uint32_t kInterleaveWidth = 32;
+__device__ __forceinline__ void ticket_to_tile(uint32_t g, uint32_t ncols, uint32_t ntiles, uint32_t width,
+                                               uint32_t* col, uint32_t* tile) {
+  if (width == 0) {
+    *col = g / ntiles;
+    *tile = g - *col * ntiles;
+    return;
+  }
+  const uint32_t per_group = width * ntiles;
+  const uint32_t group = g / per_group, r = g - group * per_group;
+  const uint32_t c0 = group * width;
+  const uint32_t w = min(width, ncols - c0);  // the last group holds what is left
+  // (tickets of a narrower last group: r runs over w * ntiles values only, because the launch's ticket
+  //  space is ncols * ntiles and earlier groups are full)
+  *tile = r / w;
+  *col = c0 + (r - *tile * w);
+}
+
 // Shared-memory scratch of the multi-split.
 struct SplitSmem {
   uint32_t* hist;  // [kTileWarps][kRadix] warp-private digit counters
