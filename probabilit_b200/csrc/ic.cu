@@ -1137,7 +1137,7 @@ int gram_tg_for(int k) { return k <= 16 ? 4 : (k <= 32 ? 8 : (k <= 64 ? 16 : 32)
 int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
   *out = nullptr;
   if (n < 1 || k < 1 || n > (int64_t)kMaxSortN || k > 8192) {
-    set_last_error("ic_plan_create: need 1 <= n < 2^30 and 1 <= k <= 8192");
+    set_last_error("ic_plan_create: need 1 <= n < 2^31 and 1 <= k <= 8192");
     return kBadShape;
   }
   IcPlan* p = new IcPlan();

@@ -688,7 +688,7 @@ scatter_rows_kernel(const uint64_t* __restrict__ keysA, const uint64_t* __restri
   const uint64_t* vals = (b == 1 ? keysA : keysB) + (size_t)col * n;
   double* outc = out + (int64_t)col * out_col_stride;
   constexpr int U = 8;
-  const uint32_t base = pos_begin + blockIdx.x * (256u * U) + threadIdx.x;  // pos_end <= n < 2^30: no overflow
+  const uint32_t base = pos_begin + blockIdx.x * (256u * U) + threadIdx.x;  // pos_end <= n < 2^31: no overflow
   uint32_t r[U];
   uint64_t v[U];
 #pragma unroll
@@ -883,8 +883,8 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
                      int ncols, int window_bits, const SortBuffers& buf, bool use_lookback,
                      cudaStream_t stream) {
   if (n == 0 || ncols <= 0) return kOk;
-  if (n > kMaxSortN) {
-    set_last_error("sort_columns_f64: n exceeds 2^30-1 rows per column");
+  if (n > kMaxSortN || (n > kMaxSortNClassic && !(use_lookback && pass_impl_tma()))) {
+    set_last_error("sort_columns_f64: n exceeds 2^31-1 rows per column (2^30-1 with PBL_PASS_IMPL=classic)");
     return kBadShape;
   }
   if (window_bits != 32 && window_bits != 64) {

@@ -9,7 +9,7 @@
 //                           followed by KeyMap's gap removal), -0.0 stored as +0.0 (they tie in
 //                           the reference; the sign travels in bit 31 of the payload and is
 //                           restored when the sorted column is read)
-//   vals  [ncols][n]  u32   source row of each key (bits 0..29), bit 31 = "was -0.0"
+//   vals  [ncols][n]  u32   source row of each key (bits 0..30), bit 31 = "was -0.0"
 //   hist  [ncols][8][256] u32   digit histograms -> exclusive bin bases
 //   status[ncols][ntiles][256] u32   look-back words: bit31 inclusive, bit30 partial, 30-bit count
 //   kminmax[ncols][4] u64   smallest / largest key of the column, largest negative / smallest positive key
@@ -41,8 +41,9 @@ constexpr int kMaxPasses = 64 / kRadixBits;
 constexpr uint32_t kFlagInclusive = 0x80000000u;
 constexpr uint32_t kFlagPartial = 0x40000000u;
 constexpr uint32_t kValueMask = 0x3FFFFFFFu;
-constexpr uint32_t kMaxSortN = 0x3FFFFFFFu;  // 30-bit counts in the look-back words
-constexpr uint32_t kRowMask = 0x3FFFFFFFu;   // payload bits that hold the row
+constexpr uint32_t kMaxSortN = 0x7FFFFFFFu;  // rows per column: the payload keeps 31 bits for the row
+constexpr uint32_t kMaxSortNClassic = 0x3FFFFFFFu;  // one-tile-per-block kernels: 30-bit counts in 32-bit look-back words
+constexpr uint32_t kRowMask = 0x7FFFFFFFu;   // payload bits that hold the row
 constexpr uint32_t kNegZeroFlag = 0x80000000u;
 
 // Look-back words of the chained scans (digit pass, fused row-window partition) are 64-bit and tagged

@@ -448,6 +448,46 @@ def test_full_size_strided_columns_against_numpy():
     plan.close()
 
 
+def test_column_longer_than_2_to_the_30_rows():
+    """Columns of more than 2^30 rows (the previous limit of the look-back words; the 8-GPU weak-scaling run
+    sorts 8e8-row columns): one column of 2^30 + 4099 doubles through the rank_scores stage.  Checked on the
+    device: sortedX == torch.sort(X), and for a million sampled rows the score is ndtri(rank / (N + 1))."""
+    import ctypes as C
+
+    import torch
+    from scipy.special import ndtri
+
+    from probabilit_b200 import _lib
+    from probabilit_b200.correlation import _IcPlan
+
+    n = (1 << 30) + 4099
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * 8 * 12:
+        pytest.skip("not enough free device memory")
+    lib = _lib.require_gpu()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(n, generator=g, device="cuda", dtype=torch.float64)
+    plan = _IcPlan(n, 1, torch.cuda.current_device())
+    plan.set_target(np.eye(1))
+    h, sp_ = plan.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.pbl_ic_stage_begin(h, sp_))
+    _lib.check(lib.pbl_ic_stage_rank_scores(h, X.data_ptr(), 1, n, 0, 1, sp_))
+    assert _lib.check(lib.pbl_ic_stage_status(h, sp_)) == 0
+    from probabilit_b200.distributed import _DevBuf
+
+    scores = torch.as_tensor(_DevBuf(plan.buffer(0)[0], (n,)), device="cuda")
+    sorted_x = torch.as_tensor(_DevBuf(plan.buffer(1)[0], (n,)), device="cuda")
+    want_sorted = torch.sort(X).values
+    assert torch.equal(sorted_x, want_sorted)
+    del want_sorted
+    idx = torch.randint(0, n, (1_000_000,), generator=g, device="cuda")
+    rank = torch.searchsorted(sorted_x, X[idx]) + 1  # untied: 1-based rank
+    got = scores[idx].cpu().numpy()
+    want = ndtri(rank.cpu().numpy() / (n + 1.0))
+    assert gpu_util.ulp_diff(got, want).max() <= 6.0
+    plan.close()
+
+
 @pytest.mark.parametrize("n,k", [(3000, 100), (2500, 257)])
 def test_wide_problem_uses_grid_cholesky(n, k):
     """k > 64: correlation / Cholesky / T are computed by the cooperative multi-block kernel."""
