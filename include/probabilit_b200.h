@@ -40,6 +40,8 @@ PBL_API int pbl_version(void);
 PBL_API const char* pbl_last_error(void);
 PBL_API int pbl_device_count(void);
 PBL_API int pbl_set_device(int device);
+/* the calling thread's current CUDA device (so that a caller can restore it after pbl_set_device) */
+PBL_API int pbl_get_device(int* device);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 PBL_API int64_t pbl_kernel_launches(void);
 

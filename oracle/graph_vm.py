@@ -66,32 +66,51 @@ def ppf(name, q, p):
     raise ValueError(name)
 
 
-def run(program, n_slots, n, inputs, outputs, uniform=None):
+ACC0, ACC1, NO_WRITE = 0x1000, 0x2000, 0x4000  # internal flags of the device form (csrc/graph.cu)
+
+
+def run(program, n_slots, n, inputs, outputs, uniform=None, dev_ops=None):
     """program: sequence of objects with .op .dst .src[4] .imm[4]; inputs / outputs: lists of
     length-n float64 arrays (outputs are written in place).  Values are float64 like on the device
-    (booleans as 0.0 / 1.0).  Returns the smallest failing CHECK tag or -1."""
+    (booleans as 0.0 / 1.0).  Returns the smallest failing CHECK tag or -1.
+
+    dev_ops (optional): the op words of the library's DEVICE FORM of the program
+    (pbl_graph_debug_translate): operands flagged ACC0 / ACC1 are taken from the previous instruction's
+    result instead of a slot, and a NO_WRITE instruction writes no slot; slots start out as None, so a read
+    of a value the translation pass wrongly dropped surfaces as an error here."""
     slots = [None] * max(n_slots, 1)
     bad = -1
+    acc = None
+    dflags = 0
 
     def operand(ins, i):
+        if (i == 0 and dflags & ACC0) or (i == 1 and dflags & ACC1):
+            return acc
         s = ins.src[i]
         return slots[s] if s >= 0 else np.full(n, ins.imm[i])
 
+    def write(dst, value):
+        nonlocal acc
+        acc = value
+        if not dflags & NO_WRITE:  # (the device form drops never-materialised slots: dst is meaningless then)
+            slots[dst] = value
+
     with np.errstate(all="ignore"):
-        for ins in program:
+        for pc, ins in enumerate(program):
+            dflags = dev_ops[pc] if dev_ops is not None else 0
             name = NAME[ins.op & 0xFF]
             flags, dst, tag, oidx = ins.op, ins.dst & 0xFF, (ins.dst >> 8) & 0xFFF, (ins.dst & 0xFFFFFFFF) >> 20
 
             def finish(value):
                 nonlocal bad
-                slots[dst] = value
+                write(dst, value)
                 if flags & 0x400 and not np.all(np.isfinite(value)):
                     bad = tag if bad < 0 else min(bad, tag)
                 if flags & 0x800:
                     outputs[oidx][:] = value
 
             if name == "LOAD":
-                slots[ins.dst] = np.array(inputs[ins.src[0]], dtype=np.float64)
+                write(ins.dst & 0xFF, np.array(inputs[ins.src[0]], dtype=np.float64))
             elif name == "STORE":
                 outputs[ins.src[1]][:] = slots[ins.src[0]]
             elif name == "CHECK":
@@ -100,7 +119,7 @@ def run(program, n_slots, n, inputs, outputs, uniform=None):
             elif name == "MOV":
                 finish(operand(ins, 0).copy())
             elif name == "UNIFORM":
-                slots[ins.dst] = uniform(ins.src[0])
+                write(ins.dst & 0xFF, uniform(ins.src[0]))
             elif name.startswith("TABLE_"):
                 if flags & 0x100:
                     q = np.array(inputs[ins.src[0]], dtype=np.float64)

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pbl_last_error": (C.c_char_p, []),
     "pbl_device_count": (C.c_int, []),
     "pbl_set_device": (C.c_int, [C.c_int]),
+    "pbl_get_device": (C.c_int, [C.POINTER(C.c_int)]),
     "pbl_kernel_launches": (_i64, []),
     "pbl_sort_profile_enable": (C.c_int, [C.c_int]),
     "pbl_sort_profile_read": (C.c_int, [C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(_i64)]),
@@ -123,6 +124,29 @@ def require_gpu():
     if lib.pbl_device_count() < 1:
         raise PblError("no CUDA device visible: probabilit_b200 has no CPU fallback")
     return lib
+
+
+class device_guard:
+    """Make `device` the calling thread's current CUDA device for the duration of a library call and restore
+    the previous one afterwards: a cached plan stays usable after the caller (or another correlator) has
+    switched devices, and the caller's later torch work keeps the device it had."""
+
+    def __init__(self, device):
+        self.device = int(device)
+
+    def __enter__(self):
+        lib = load()
+        prev = C.c_int(-1)
+        check(lib.pbl_get_device(C.byref(prev)), "pbl_get_device")
+        self.prev = prev.value
+        if self.prev != self.device:
+            check(lib.pbl_set_device(self.device), "pbl_set_device")
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0 and self.prev != self.device:
+            load().pbl_set_device(self.prev)
+        return False
 
 
 def kernel_launches():

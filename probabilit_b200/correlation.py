@@ -178,11 +178,11 @@ class _IcPlan:
     def __init__(self, n, k, device, col_batch=0, rows_only=False):
         self.lib = _lib.require_gpu()
         self.n, self.k, self.device = n, k, device
-        _lib.check(self.lib.pbl_set_device(device), "pbl_set_device")
         h = C.c_void_p()
-        st = _lib.check(
-            self.lib.pbl_ic_plan_create_ex(n, k, col_batch, 1 if rows_only else 0, C.byref(h)),
-            "pbl_ic_plan_create")
+        with _lib.device_guard(device):
+            st = _lib.check(
+                self.lib.pbl_ic_plan_create_ex(n, k, col_batch, 1 if rows_only else 0, C.byref(h)),
+                "pbl_ic_plan_create")
         if st != _lib.STATUS_OK:
             raise ValueError(_lib.last_error())
         self.handle = h
@@ -284,7 +284,9 @@ class _PlanCorrelator(Correlator):
 
     def _run(self, plan, x_ptr, xrs, xcs, y_ptr, yrs, ycs, stream):
         fn = getattr(plan.lib, self._entry)
-        st = _lib.check(fn(plan.handle, C.c_void_p(x_ptr), xrs, xcs, C.c_void_p(y_ptr), yrs, ycs, stream), self._entry)
+        with _lib.device_guard(plan.device):  # the plan's device, whatever the caller's current one is
+            st = _lib.check(fn(plan.handle, C.c_void_p(x_ptr), xrs, xcs, C.c_void_p(y_ptr), yrs, ycs, stream),
+                            self._entry)
         self._raise(st)
 
     # ------------------------------------------------------------------ the transform
@@ -298,7 +300,9 @@ class _PlanCorrelator(Correlator):
         N, K = self._validate_X(X)
         if _is_cuda_tensor(X):
             return self._call_device(X, N, K)
-        return self._call_host(X, N, K, out)
+        _lib.require_gpu()
+        with _lib.device_guard(0 if self.device is None else int(self.device)):
+            return self._call_host(X, N, K, out)
 
     def _call_host(self, X, N, K, out=None):
         lib = _lib.require_gpu()
@@ -365,9 +369,10 @@ class _PlanCorrelator(Correlator):
         if N <= K:
             raise ValueError(f"The matrix X must have rows > columns. Got shape: {(N, K)}")
         device = 0 if self.device is None else int(self.device)
-        plan = self._get_plan(N, K, device)
-        Y = DeviceColumns(N, K)
-        self._run(plan, X.ptr, 1, N, Y.ptr, 1, N, None)
+        with _lib.device_guard(device):
+            plan = self._get_plan(N, K, device)
+            Y = DeviceColumns(N, K)
+            self._run(plan, X.ptr, 1, N, Y.ptr, 1, N, None)
         return Y
 
 
@@ -417,11 +422,18 @@ def corrcoef(X, *, spearman=False, device=None):
     else:
         cols, keep = as_device_columns(X)
         N, K, ptr, rs, cs = cols.n, cols.k, cols.ptr, 1, cols.n
-    plan = _IcPlan(N, K, 0 if device is None else int(device), rows_only=not spearman)
+    device = 0 if device is None else int(device)
+    stream = None
+    if _is_cuda_tensor(X):  # ordered after whatever produced X on the caller's current stream
+        import torch
+
+        stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+    plan = _IcPlan(N, K, device, rows_only=not spearman)
     try:
         out = np.empty((K, K))
-        st = _lib.check(lib.pbl_corrcoef_f64(plan.handle, C.c_void_p(ptr), rs, cs, 1 if spearman else 0,
-                                             out.ctypes.data, None), "pbl_corrcoef_f64")
+        with _lib.device_guard(device):
+            st = _lib.check(lib.pbl_corrcoef_f64(plan.handle, C.c_void_p(ptr), rs, cs, 1 if spearman else 0,
+                                                 out.ctypes.data, stream), "pbl_corrcoef_f64")
         _raise_for_status(st)
     finally:
         plan.close()

@@ -51,6 +51,12 @@ int pbl_set_device(int device) {
   return kOk;
 }
 
+int pbl_get_device(int* device) {
+  if (!device) return kBadShape;
+  PBL_CUDA_CHECK(cudaGetDevice(device));
+  return kOk;
+}
+
 int pbl_device_malloc(void** ptr, uint64_t bytes) {
   PBL_CUDA_CHECK(cudaMalloc(ptr, bytes ? bytes : 16));
   return kOk;

@@ -461,15 +461,19 @@ post_sort_kernel(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* va
 
 #include "post_tma.cuh"
 
-// PBL_POST_IMPL=classic selects post_sort_kernel above (kept for A/B measurements and for the no-look-back
-// debug path); the default is the persistent bulk-async kernel (post_tma.cuh)
-bool post_impl_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PBL_POST_IMPL");
-    v = (e && e[0] == 'c') ? 0 : 1;
-  }
-  return v == 1;
+// Which consumer kernel follows the sorts of columns of n rows.  The persistent bulk-async kernel
+// (post_tma.cuh) is the faster one while runs of equal window values are short (0.2 keys per window value at
+// n = 1e8); the one-tile-per-block kernel above (2048-key tiles, run extents from ballot masks) wins on the
+// long columns of a multi-GPU call, whose windows are dense (1.5 keys per value at n = 8e8: 108 vs 127 ms
+// per rank_scores of 2 x 8e8 keys, profiles/r2_narrow_launch_experiments.txt).
+// PBL_POST_IMPL=classic|tma forces one (A/B measurements; "classic" is also the no-look-back debug path);
+// PBL_POST_CLASSIC_ABOVE=<rows> moves the switch-over.
+bool post_impl_tma(uint32_t n) {
+  const char* e = getenv("PBL_POST_IMPL");  // (read per call: the parity tests switch it between plans)
+  if (e && e[0]) return e[0] != 'c';
+  uint64_t above = 300000000ull;
+  if (const char* a = getenv("PBL_POST_CLASSIC_ABOVE")) above = strtoull(a, nullptr, 10);
+  return !(n > above && n <= kMaxSortNClassic);
 }
 
 // ======================================================================================
@@ -1140,19 +1144,21 @@ int ic_plan_create(int64_t n, int k, int col_batch, int flags, IcPlan** out) {
     set_last_error("ic_plan_create: need 1 <= n < 2^31 and 1 <= k <= 8192");
     return kBadShape;
   }
+  int device = 0;
+  size_t free_b = 0, total_b = 0;
+  PBL_CUDA_CHECK(cudaGetDevice(&device));  // (before the plan exists: an early CUDA failure leaks nothing)
+  PBL_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   IcPlan* p = new IcPlan();
   p->n = n;
   p->k = k;
   p->rows_only = (flags & 1) != 0;
-  PBL_CUDA_CHECK(cudaGetDevice(&p->device));
+  p->device = device;
   const char* lb = getenv("PBL_SORT_LOOKBACK");
   p->use_lookback = !(lb && lb[0] == '0');
   const char* wb = getenv("PBL_WINDOW_BITS");
   p->window_bits = (wb && atoi(wb) == 64) ? 64 : 32;
 
   // column batch: as many columns per launch as fit in ~45% of free memory
-  size_t free_b = 0, total_b = 0;
-  PBL_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   const size_t fixed = (size_t)2 * k * n * 8;  // sortedX + scores
   const size_t per_col = (size_t)n * 24 + sort_status_bytes(1, (uint32_t)n) + 16384;
   if (col_batch <= 0) {
@@ -1358,7 +1364,7 @@ int ic_stage_rank_scores(IcPlan* p, const double* X, int64_t row_stride, int64_t
     uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), 1, p->use_lookback, kPostTile, &shift, &ntiles, &counter,
                                   &epoch, stream));
-    if (p->use_lookback && post_impl_tma()) {
+    if (p->use_lookback && post_impl_tma(n)) {
       if (ranks_only)
         PBL_RETURN_IF(launch_post_tma<2>(p, c, nb, shift, epoch, counter, stream));
       else
@@ -1470,7 +1476,7 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     uint32_t epoch = 0;
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), row_stride, p->use_lookback, kPostTile, &shift, &ntiles,
                                   &counter, &epoch, stream));
-    if (p->use_lookback && post_impl_tma()) {
+    if (p->use_lookback && post_impl_tma(n)) {
       PBL_RETURN_IF(launch_post_tma<1>(p, c, nb, shift, epoch, counter, stream));
     } else {
       post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
@@ -1585,9 +1591,23 @@ int ic_plan_run_host(IcPlan* p, const double* Xh, int64_t xrs, int64_t xcs, doub
     PBL_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     p->events.push_back(e);
   }
+  // every exit -- including the early error returns below -- first drains the copy stream: its copies target
+  // the caller's host buffers and dX / dY, which the caller may reuse or free as soon as this returns
+  struct DrainCopies {
+    cudaStream_t s;
+    ~DrainCopies() { cudaStreamSynchronize(s); }
+  } drain{p->copy_stream};
+  while ((int)p->events.size() < 2 * nb + 1) {
+    cudaEvent_t e;
+    PBL_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->events.push_back(e);
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     PBL_CUDA_CHECK(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), stream));
-    // the copy stream must not run ahead of work queued earlier on `stream` (e.g. a previous call's D2H)
+    // the copy stream must not run ahead of work queued earlier on `stream` (e.g. the caller's last use of
+    // dX / dY, or the first attempt's sorts that still read dX)
+    PBL_CUDA_CHECK(cudaEventRecord(p->events[2 * nb], stream));
+    PBL_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->events[2 * nb], 0));
     for (int b = 0; b < nb; ++b) {
       const int c0 = b * bc, nc = std::min(bc, k - c0);
       PBL_CUDA_CHECK(cudaMemcpyAsync(dX + (size_t)c0 * n, Xh + (size_t)c0 * n, (size_t)nc * n * 8,

@@ -800,6 +800,8 @@ class _Emitter:
                 if kind == "q":
                     ins.src[0] = value
                 elif kind == "check":
+                    if value > 0xFFF:  # the fused CHECK carries a 12-bit node tag
+                        raise NotImplementedError(f"graph has more than {0xFFF + 1} checked nodes")
                     ins.dst |= (value & 0xFFF) << 8
                 elif kind == "store":
                     ins.dst |= value << 20

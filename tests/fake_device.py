@@ -41,9 +41,31 @@ def fake_as_device_columns(q):
     return cols, cols
 
 
+def device_form(prog):
+    """The library's device form of an ABI program: (program, op words with the internal flags, slot count)."""
+    import ctypes as C
+
+    from probabilit_b200 import _lib
+
+    lib = _lib.load()
+    ops = (C.c_int32 * len(prog))()
+    out = (_lib.GraphInstr * len(prog))()
+    ns = C.c_int32(0)
+    assert lib.pbl_graph_debug_translate(prog, len(prog), out, ops, C.byref(ns)) == 0
+    assert sorted(o & 0xFFF for o in ops) == sorted(i.op & 0xFFF for i in prog)  # a permutation of the same work
+    return out, list(ops), ns.value
+
+
+DEVICE_FORM = False  # True: run the VM on the library's device form of the program (accumulator / dead-store flags)
+
+
 def fake_run_program(em, n, row0, inputs, outputs):
     prog, n_slots = em.assemble()
-    return graph_vm.run(list(prog), n_slots, n, [_REGISTRY[p] for p in inputs], [_REGISTRY[p] for p in outputs])
+    dev_ops = None
+    if DEVICE_FORM and len(prog):
+        prog, dev_ops, n_slots = device_form(prog)
+    return graph_vm.run(list(prog), n_slots, n, [_REGISTRY[p] for p in inputs], [_REGISTRY[p] for p in outputs],
+                        dev_ops=dev_ops)
 
 
 def install(monkeypatch):

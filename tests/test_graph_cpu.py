@@ -124,3 +124,50 @@ def test_distribution_constructors(monkeypatch):
     tn = d.TruncatedNormal(loc=3, scale=0.5, low=2.5, high=4).sample_from_quantiles(q)
     assert tn.min() >= 2.5 and tn.max() <= 4
     assert probabilit_b200.Distribution is m.Distribution and probabilit_b200.PERT is d.PERT
+
+
+@pytest.mark.parametrize("name", list(graph_recipes.RECIPES))
+def test_device_form_of_the_program_preserves_the_results(name, monkeypatch):
+    """The library translates the ABI bytecode into its device form before launching (csrc/graph.cu:
+    operands taken from the accumulator, dead slot stores skipped).  The translation is host code: run the
+    oracle VM on the device form and require the reference's vectors."""
+    import probabilit_b200.modeling as m
+
+    fake_device.install(monkeypatch)
+    monkeypatch.setattr(fake_device, "DEVICE_FORM", True)
+    recipe, n = graph_recipes.RECIPES[name]
+    sink, named = recipe(m)
+    sink.sample_from_quantiles(GOLDEN[f"{name}__quantiles"], correlator=OracleImanConover)
+    for label, node in named:
+        np.testing.assert_array_equal(node.samples_, GOLDEN[f"{name}__{label}"], err_msg=f"{name}:{label}")
+
+
+def test_device_form_chains_the_mutual_fund_graph_through_the_accumulator(monkeypatch):
+    """README example 3: ppf -> MUL -> ADD per year.  With only the sink retained every interest rate and every
+    product is consumed by the next instruction: no slot traffic except the running total."""
+    import ctypes as C
+
+    import probabilit_b200.modeling as m
+    from probabilit_b200 import _lib
+
+    fake_device.install(monkeypatch)
+    seen = {}
+
+    def capture(em, n, row0, inputs, outputs):
+        prog, n_slots = em.assemble()
+        seen["prog"], seen["ops"], seen["n_slots"] = fake_device.device_form(prog)
+        seen["abi_slots"] = n_slots
+        return fake_device.fake_run_program(em, n, row0, inputs, outputs)
+
+    monkeypatch.setattr(m, "_run_program", capture)
+    sink, _ = graph_recipes.mutual_fund(m)
+    q = np.random.default_rng(0).random((50, 20))
+    sink.sample_from_quantiles(q, gc_strategy=[])
+    ops = seen["ops"]
+    names = [o & 0xFF for o in ops]
+    assert names.count(16) == 20  # the norm ppfs
+    acc = sum(1 for o in ops if o & 0x3000)
+    no_write = sum(1 for o in ops if o & 0x4000)
+    # 20 x (ppf -> MUL via the accumulator -> ADD via the accumulator); only the running total lives in a slot
+    assert acc >= 40 and no_write >= 40, (acc, no_write, len(ops), [hex(o) for o in ops])
+    assert seen["abi_slots"] >= 20 and seen["n_slots"] <= 2, (seen["abi_slots"], seen["n_slots"])
