@@ -333,38 +333,55 @@ __device__ __forceinline__ void uniform_rows(uint64_t seed, const uint64_t (&gpa
 // tail code runs ceil(#tails / 32) times instead of R times (R = 4: 35 tails on average -> 1-2 rounds instead
 // of 4).  Values are bit-identical to ndtri() (ndtri.cuh): same operations on the same operands.
 // All 32 lanes must call it together; `queue` holds 32 * R doubles private to the warp.
+// The Cephes coefficient tables live in CONSTANT memory here: fp64 instructions take a constant-bank operand
+// directly, whereas a literal costs two UMOVs (a 64-bit immediate does not fit the instruction) -- in the ncu
+// capture of the first version of this kernel 16 % of all executed instructions were UMOVs.
+__constant__ double kNdP0[5] = {-5.99633501014107895267E1, 9.80010754185999661536E1, -5.66762857469070293439E1,
+                                1.39312609387279679503E1, -1.23916583867381258016E0};
+__constant__ double kNdQ0[8] = {1.95448858338141759834E0, 4.67627912898881538453E0,  8.63602421390890590575E1,
+                                -2.25462687854119370527E2, 2.00260212380060660359E2, -8.20372256168333339912E1,
+                                1.59056225126211695515E1, -1.18331621121330003142E0};
+__constant__ double kNdP1[9] = {4.05544892305962419923E0,  3.15251094599893866154E1,  5.71628192246421288162E1,
+                                4.40805073893200834700E1,  1.46849561928858024014E1,  2.18663306850790267539E0,
+                                -1.40256079171354495875E-1, -3.50424626827848203418E-2, -8.57456785154685413611E-4};
+__constant__ double kNdQ1[8] = {1.57799883256466749731E1,  4.53907635128879210584E1,  4.13172038254672030440E1,
+                                1.50425385692907503408E1,  2.50464946208309415979E0,  -1.42182922854787788574E-1,
+                                -3.80806407691578277194E-2, -9.33259480895457427372E-4};
+__constant__ double kNdP2[9] = {3.23774891776946035970E0,  6.91522889068984211695E0,  3.93881025292474443415E0,
+                                1.33303460815807542389E0,  2.01485389549179081538E-1, 1.23716634817820021358E-2,
+                                3.01581553508235416007E-4, 2.65806974686737550832E-6, 6.23974539184983293730E-9};
+__constant__ double kNdQ2[8] = {6.02427039364742014255E0,  3.67983563856160859403E0,  1.37702099489081330271E0,
+                                2.16236993594496635890E-1, 1.34204006088543189037E-2, 3.28014464682127739104E-4,
+                                2.89247864745380683936E-6, 6.79019408009981274425E-9};
+template <int N>
+__device__ __forceinline__ double ndc_polevl(double x, const double* c) {  // c: a __constant__ table
+  double r = c[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) r = nd_add(nd_mul(r, x), c[i]);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ double ndc_p1evl(double x, const double* c) {
+  double r = nd_add(x, c[0]);
+#pragma unroll
+  for (int i = 1; i < N; ++i) r = nd_add(nd_mul(r, x), c[i]);
+  return r;
+}
 __device__ __forceinline__ double ndtri_central(double y) {  // y = q - 0.5
-  const double P0[5] = {-5.99633501014107895267E1, 9.80010754185999661536E1, -5.66762857469070293439E1,
-                        1.39312609387279679503E1, -1.23916583867381258016E0};
-  const double Q0[8] = {1.95448858338141759834E0, 4.67627912898881538453E0,  8.63602421390890590575E1,
-                        -2.25462687854119370527E2, 2.00260212380060660359E2, -8.20372256168333339912E1,
-                        1.59056225126211695515E1, -1.18331621121330003142E0};
   const double s2pi = 2.50662827463100050242E0;
   const double y2 = nd_mul(y, y);
-  const double x = nd_add(y, nd_mul(y, __ddiv_rn(nd_mul(y2, nd_polevl(y2, P0)), nd_p1evl(y2, Q0))));
+  const double x = nd_add(y, nd_mul(y, __ddiv_rn(nd_mul(y2, ndc_polevl<5>(y2, kNdP0)), ndc_p1evl<8>(y2, kNdQ0))));
   return nd_mul(x, s2pi);
 }
 __device__ __noinline__ double ndtri_tail(double y) {  // 0 < y <= exp(-2); returns |ndtri|
-  const double P1[9] = {4.05544892305962419923E0,  3.15251094599893866154E1,  5.71628192246421288162E1,
-                        4.40805073893200834700E1,  1.46849561928858024014E1,  2.18663306850790267539E0,
-                        -1.40256079171354495875E-1, -3.50424626827848203418E-2, -8.57456785154685413611E-4};
-  const double Q1[8] = {1.57799883256466749731E1,  4.53907635128879210584E1,  4.13172038254672030440E1,
-                        1.50425385692907503408E1,  2.50464946208309415979E0,  -1.42182922854787788574E-1,
-                        -3.80806407691578277194E-2, -9.33259480895457427372E-4};
-  const double P2[9] = {3.23774891776946035970E0,  6.91522889068984211695E0,  3.93881025292474443415E0,
-                        1.33303460815807542389E0,  2.01485389549179081538E-1, 1.23716634817820021358E-2,
-                        3.01581553508235416007E-4, 2.65806974686737550832E-6, 6.23974539184983293730E-9};
-  const double Q2[8] = {6.02427039364742014255E0,  3.67983563856160859403E0,  1.37702099489081330271E0,
-                        2.16236993594496635890E-1, 1.34204006088543189037E-2, 3.28014464682127739104E-4,
-                        2.89247864745380683936E-6, 6.79019408009981274425E-9};
   const double x = __dsqrt_rn(nd_mul(-2.0, log(y)));
   const double x0 = nd_add(x, -__ddiv_rn(log(x), x));
   const double z = __ddiv_rn(1.0, x);
   double x1;
   if (x < 8.0)
-    x1 = __ddiv_rn(nd_mul(z, nd_polevl(z, P1)), nd_p1evl(z, Q1));
+    x1 = __ddiv_rn(nd_mul(z, ndc_polevl<9>(z, kNdP1)), ndc_p1evl<8>(z, kNdQ1));
   else
-    x1 = __ddiv_rn(nd_mul(z, nd_polevl(z, P2)), nd_p1evl(z, Q2));
+    x1 = __ddiv_rn(nd_mul(z, ndc_polevl<9>(z, kNdP2)), ndc_p1evl<8>(z, kNdQ2));
   return nd_add(x0, -x1);
 }
 template <int R>
