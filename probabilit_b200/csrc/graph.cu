@@ -268,6 +268,8 @@ struct GraphArgs {
   const double* const* inputs;
   double* const* outputs;
   int* first_nonfinite;
+  const int32_t* row_inputs;  // indices into inputs[] of the columns that are read row by row (not tables)
+  int n_row_inputs;
 };
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
@@ -473,6 +475,14 @@ __global__ void __launch_bounds__(kGraphBlockR, 4) graph_eval_kernel(const Graph
       rw.active[2 * p] = rw.first[p] >= 0 && rw.first[p] < g.n;
       rw.active[2 * p + 1] = rw.first[p] + 1 < g.n;
       gpair[p] = (g_even + (uint64_t)rp) >> 1;
+    }
+    // the quantile / sample columns of this chunk are asked for now (HBM -> L2): the loads are fused into the
+    // instructions that consume them, one column at a time, and would each expose a full HBM round trip
+    for (int i = 0; i < g.n_row_inputs; ++i) {
+      const double* col = g.inputs[g.row_inputs[i]];
+#pragma unroll
+      for (int p = 0; p < R / 2; ++p)
+        if (rw.active[2 * p + 1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + rw.first[p] + 1));
     }
     double acc[R];
 #pragma unroll
@@ -884,14 +894,27 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
     return kBadShape;
   }
 
-  // one staging buffer (cached, grown on demand): [flag | program | input pointers | output pointers]
+  // input columns that are read row by row (LOAD / fused quantile loads), for the kernel's L2 prefetch
+  std::vector<int32_t> row_inputs;
+  {
+    std::vector<char> seen((size_t)std::max(n_inputs, 1), 0);
+    for (const pbl::DevInstr& d : dev_prog)
+      if ((d.op & 0xFF) == PBL_OP_LOAD || (d.op & PBL_GRAPH_Q_INPUT))
+        if (!seen[(size_t)d.src[0]]) {
+          seen[(size_t)d.src[0]] = 1;
+          row_inputs.push_back(d.src[0]);
+        }
+  }
+  // one staging buffer (cached, grown on demand): [flag | program | input pointers | output pointers | row inputs]
   const size_t off_prog = 64, off_in = off_prog + prog_bytes, off_out = off_in + (size_t)n_inputs * 8;
-  const size_t total = off_out + (size_t)n_outputs * 8 + 16;
+  const size_t off_rows = off_out + (size_t)n_outputs * 8;
+  const size_t total = off_rows + row_inputs.size() * 4 + 16;
   std::vector<unsigned char> host(total, 0);
   *reinterpret_cast<int*>(host.data()) = 0x7FFFFFFF;
   memcpy(host.data() + off_prog, dev_prog.data(), prog_bytes);
   if (n_inputs) memcpy(host.data() + off_in, inputs_dev, (size_t)n_inputs * 8);
   if (n_outputs) memcpy(host.data() + off_out, outputs_dev, (size_t)n_outputs * 8);
+  if (!row_inputs.empty()) memcpy(host.data() + off_rows, row_inputs.data(), row_inputs.size() * 4);
   static std::mutex mu;
   static std::map<int, std::pair<unsigned char*, size_t>> staging;  // per device
   static bool attr_set[2] = {false, false};
@@ -918,6 +941,8 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
   a.inputs = reinterpret_cast<const double* const*>(dev + off_in);
   a.outputs = reinterpret_cast<double* const*>(dev + off_out);
   a.first_nonfinite = reinterpret_cast<int*>(dev);
+  a.row_inputs = reinterpret_cast<const int32_t*>(dev + off_rows);
+  a.n_row_inputs = (int)row_inputs.size();
   if (!attr_set[R == 4]) {
     if (R == 4)
       PBL_CUDA_CHECK(cudaFuncSetAttribute(pbl::graph_eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
