@@ -147,10 +147,11 @@ __device__ __forceinline__ void tma_tile(const TmaArgs& a, const TmaSmem& sm, co
 #pragma unroll
       for (int u = 0; u < ITEMS; ++u) d[u] = (FULL || pos0 + u * 32 < nvalid) ? ld_stream_f64(colp + u * step) : 0.0;
     }
+    const FusedKeyMap fmap = fused_key_map(map);
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u) {
       bool nz;
-      key[u] = compact_key(key_of_double(d[u], &nz), map);
+      key[u] = compact_key_of_double(d[u], fmap, &nz);
       negzero |= (nz ? 1u : 0u) << u;
     }
   }

@@ -145,6 +145,33 @@ __device__ __forceinline__ uint64_t compact_key(uint64_t key, const KeyMap& m) {
   const uint64_t base = key > kZeroKey ? m.g : (key == kZeroKey ? m.g0 : m.kmin);
   return key - base;
 }
+// compact_key(key_of_double(d)) in one go, on the two 32-bit halves of the double (the digit pass that reads
+// the caller's doubles spent a quarter of its instructions on 64-bit compares and selects here):
+//   negative:  key = ~bits,              a = key - kmin
+//   +-0.0:     key = kZeroKey,           a = neg_al            (*neg_zero: it was -0.0)
+//   positive:  key = bits ^ 2^63,        a = key - g
+// A FusedKeyMap holds the three constants for either window (exact: a = key).
+struct FusedKeyMap {
+  uint64_t base_neg, base_pos, zero_val;
+};
+__device__ __forceinline__ FusedKeyMap fused_key_map(const KeyMap& m) {
+  FusedKeyMap f;
+  f.base_neg = m.exact ? 0ull : m.kmin;
+  f.base_pos = m.exact ? 0ull : m.g;
+  f.zero_val = m.exact ? kZeroKey : m.neg_al;
+  return f;
+}
+__device__ __forceinline__ uint64_t compact_key_of_double(double d, const FusedKeyMap& f, bool* neg_zero) {
+  const uint32_t hi = (uint32_t)__double2hiint(d), lo = (uint32_t)__double2loint(d);
+  const uint32_t m = (uint32_t)((int32_t)hi >> 31);  // all ones for a set sign bit
+  const bool neg = (int32_t)hi < 0;
+  const bool zero = ((hi & 0x7FFFFFFFu) | lo) == 0u;
+  const uint32_t kh = hi ^ (m | 0x80000000u), kl = lo ^ m;
+  const uint64_t key = ((uint64_t)kh << 32) | kl;
+  const uint64_t a = key - (neg ? f.base_neg : f.base_pos);
+  *neg_zero = neg && zero;
+  return zero ? f.zero_val : a;
+}
 __device__ __forceinline__ uint64_t expand_key(uint64_t a, const KeyMap& m) {
   if (m.exact) return a;
   return a > m.neg_al ? a + m.g : (a == m.neg_al ? kZeroKey : a + m.kmin);
