@@ -124,6 +124,13 @@ PBL_API int pbl_permcorr_steps(pbl_ic_plan* plan, double* Y_dev, const int32_t* 
                                void* stream);
 PBL_API int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr);
 
+/* dst[r * d_row_stride + c * d_col_stride] = src[r * s_row_stride + c * s_col_stride] for an (n, k) fp64 matrix on
+ * the device (element strides; the buffers must not overlap).  Layout conversion around the correlators that
+ * work column-major inside: `X.copy()` keeps the caller's C order in the reference (correlation.py:830-831), so
+ * the result of PermutationCorrelator goes back row-major without a host-side transpose.  Asynchronous. */
+PBL_API int pbl_copy_strided_f64(const double* src_dev, int64_t s_row_stride, int64_t s_col_stride, double* dst_dev,
+                                 int64_t d_row_stride, int64_t d_col_stride, int64_t n, int32_t k, void* stream);
+
 /* Verification helper: np.corrcoef(X, rowvar=False) (spearman == 0) or the Spearman matrix
  * (Pearson correlation of scipy.stats.rankdata's average ranks; the Spearman mode of CorrelationMatrix,
  * correlation.py:835-837) of device-resident X into HOST out[k*k].  Spearman needs a plan with sort

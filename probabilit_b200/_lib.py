@@ -59,6 +59,7 @@ SIGNATURES = {
     "pbl_permcorr_corr": (C.c_int, [_vp, _pd]),
     "pbl_ic_plan_run_host": (C.c_int, [_vp, _pd, _i64, _i64, _pd, _i64, _i64, _pd, _pd, _vp]),
     "pbl_corrcoef_f64": (C.c_int, [_vp, _pd, _i64, _i64, _i32, _pd, _vp]),
+    "pbl_copy_strided_f64": (C.c_int, [_pd, _i64, _i64, _pd, _i64, _i64, _i64, _i32, _vp]),
     "pbl_iman_conover_f64": (C.c_int, [_pd, _i64, _i32, _i64, _i64, _pd, _pd, _i64, _i64]),
     "pbl_ic_stage_begin": (C.c_int, [_vp, _vp]),
     "pbl_ic_stage_rank_scores": (C.c_int, [_vp, _pd, _i64, _i64, _i32, _i32, _vp]),

@@ -453,6 +453,17 @@ class SwapIndexGenerator:
         self.indices = np.arange(n)
         self.permutation = self.rng.permutation(self.indices)
 
+    def snapshot(self):
+        """State to come back to with restore(): the unconsumed part of the current permutation (a view: draws
+        re-slice it, a redraw replaces it, nothing writes into it) and the generator's state."""
+        import copy
+
+        return self.permutation, copy.deepcopy(self.rng.bit_generator.state)
+
+    def restore(self, snap):
+        self.permutation, state = snap
+        self.rng.bit_generator.state = state
+
     def __call__(self, size):
         assert size >= 1
         size = min(size, len(self.indices) // 2)
@@ -517,7 +528,6 @@ class PermutationCorrelator(Correlator):
             raise ValueError("`X` must be a 2D numpy array.")
         if self.correlation_type not in ("pearson", "spearman"):
             raise ValueError(f"`correlation_type` must be in ('pearson', 'spearman'), got {self.correlation_type}")
-        import copy as _copy
         from ._device import DeviceColumns
 
         lib = _lib.require_gpu()
@@ -529,12 +539,20 @@ class PermutationCorrelator(Correlator):
         device = 0 if self.device is None else int(self.device)
         spearman = self.correlation_type == "spearman"
         plan = _IcPlan(N, K, device, rows_only=not spearman)
-        dX = DeviceColumns.from_host(X)
+        # X goes to the device in the layout it has (the begin stage reads any strides and makes the
+        # column-major working copy itself); the result comes back in C order like the reference's X.copy()
+        Xh = X if (X.dtype == np.float64 and (X.flags.c_contiguous or X.flags.f_contiguous)) \
+            else np.ascontiguousarray(X, dtype=np.float64)
+        xrs, xcs = _strides_elems(Xh.shape, Xh.strides, 8)
+        raw = C.c_void_p()
         dY = DeviceColumns(N, K)
         try:
+            _lib.check(lib.pbl_device_malloc(C.byref(raw), max(Xh.nbytes, 16)), "pbl_device_malloc")
+            if Xh.nbytes:
+                _lib.check(lib.pbl_memcpy_h2d(raw, Xh.ctypes.data, Xh.nbytes, None), "pbl_memcpy_h2d")
             target = np.ascontiguousarray(self.C, dtype=np.float64)
             weights = np.ascontiguousarray(self.weights, dtype=np.float64)
-            st = _lib.check(lib.pbl_permcorr_begin(plan.handle, C.c_void_p(dX.ptr), 1, N, C.c_void_p(dY.ptr),
+            st = _lib.check(lib.pbl_permcorr_begin(plan.handle, raw, xrs, xcs, C.c_void_p(dY.ptr),
                                                    1 if spearman else 0, target.ctypes.data, weights.ctypes.data,
                                                    None), "pbl_permcorr_begin")
             if st == _lib.STATUS_NOT_PD:
@@ -548,7 +566,7 @@ class PermutationCorrelator(Correlator):
                 last = iteration + iters_per_chunk - 1
                 if self.iters:
                     last = min(last, self.iters)
-                snapshot = _copy.deepcopy(swaps_gen)  # to replay the exact consumption on early exit
+                snapshot = swaps_gen.snapshot()  # to replay the exact consumption on early exit
                 cols, offs, cnts, idx, counts_per_iter = [], [], [], [], []
                 total = 0
                 for it in range(iteration, last + 1):
@@ -578,18 +596,24 @@ class PermutationCorrelator(Correlator):
                     self._print_progress(iteration, last, errors, int(nerr.value), counts_per_iter, bool(conv.value))
                 if conv.value:
                     # leave self.rng where the reference would have left it: replay the consumed draws only
-                    swaps_gen = snapshot
+                    swaps_gen.restore(snapshot)
                     for t in range(int(done.value)):
                         swaps_gen(counts_per_iter[t // K])
                     self.rng = swaps_gen.rng
                     finished = True
                 iteration = last + 1
-            out = dY.to_host()
+            # corr_mat.X is X.copy(): C order (reference :831) -- transposed on the device, into the input's
+            # staging buffer (dead since the begin stage), then one contiguous copy to the host
+            result = np.empty((N, K), dtype=np.float64)
+            _lib.check(lib.pbl_copy_strided_f64(C.c_void_p(dY.ptr), 1, N, raw, K, 1, N, K, None), "pbl_copy_strided_f64")
+            if result.nbytes:
+                _lib.check(lib.pbl_memcpy_d2h(result.ctypes.data, raw, result.nbytes, None), "pbl_memcpy_d2h")
+            _lib.check(lib.pbl_stream_synchronize(None), "pbl_stream_synchronize")
         finally:
-            dX.free()
+            if raw.value:
+                lib.pbl_device_free(raw)
             dY.free()
             plan.close()
-        result = np.ascontiguousarray(out)  # corr_mat.X is X.copy(): C order (reference :831)
         return result if result.dtype == X.dtype else result.astype(X.dtype)
 
     def _print_progress(self, first, last, errors, nerr, counts, converged):

@@ -216,6 +216,12 @@ int pbl_permcorr_corr(pbl_ic_plan* plan, double* corr) {
   return pbl::permcorr_read_corr(plan->impl, corr);
 }
 
+int pbl_copy_strided_f64(const double* src, int64_t srs, int64_t scs, double* dst, int64_t drs, int64_t dcs, int64_t n,
+                         int32_t k, void* stream) {
+  if (n < 0 || k < 0 || (n > 0 && k > 0 && (!src || !dst))) return kBadShape;
+  return pbl::copy_strided(src, srs, scs, dst, drs, dcs, n, k, (cudaStream_t)stream);
+}
+
 int pbl_corrcoef_f64(pbl_ic_plan* plan, const double* X, int64_t xrs, int64_t xcs, int32_t spearman, double* out,
                      void* stream) {
   if (!plan || !X || !out) return kBadShape;

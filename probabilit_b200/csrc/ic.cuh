@@ -93,6 +93,10 @@ int permcorr_read_corr(IcPlan* plan, double* corr_host);
 int corrcoef_run(IcPlan* plan, const double* X, int64_t xrs, int64_t xcs, int spearman, double* out_host,
                  cudaStream_t stream);
 
+// (n, k) fp64 matrix from one strided layout to another on the device (non-overlapping buffers)
+int copy_strided(const double* src, int64_t srs, int64_t scs, double* dst, int64_t drs, int64_t dcs, int64_t n, int k,
+                 cudaStream_t stream);
+
 // Cholesky correlator (reference correlation.py:205-285); synchronous like ic_plan_run.
 int cholesky_correlator_run(IcPlan* plan, const double* X, int64_t x_row_stride, int64_t x_col_stride,
                             double* Y, int64_t y_row_stride, int64_t y_col_stride, cudaStream_t stream);

@@ -340,4 +340,43 @@ int permcorr_read_corr(IcPlan* p, double* corr_host) {
   return kOk;
 }
 
+// Layout conversion of an (n, k) matrix: a block moves a tile of 32 rows x 32 columns through shared memory,
+// reading along the source's unit-stride dimension and writing along the destination's, so that both sides are
+// coalesced when one layout is row-major and the other column-major.
+__global__ void __launch_bounds__(256)
+copy_strided_kernel(const double* __restrict__ src, int64_t srs, int64_t scs, double* __restrict__ dst, int64_t drs,
+                    int64_t dcs, int64_t n, int k) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = (int)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool src_rows_fast = srs <= scs;  // consecutive rows are adjacent in the source
+  const bool dst_rows_fast = drs <= dcs;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + (src_rows_fast ? tx : i);
+    const int c = c0 + (src_rows_fast ? i : tx);
+    if (r < n && c < k) tile[(int)(r - r0)][c - c0] = src[r * srs + (int64_t)c * scs];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + (dst_rows_fast ? tx : i);
+    const int c = c0 + (dst_rows_fast ? i : tx);
+    if (r < n && c < k) dst[r * drs + (int64_t)c * dcs] = tile[(int)(r - r0)][c - c0];
+  }
+}
+
+int copy_strided(const double* src, int64_t srs, int64_t scs, double* dst, int64_t drs, int64_t dcs, int64_t n, int k,
+                 cudaStream_t stream) {
+  if (n == 0 || k == 0) return kOk;
+  const int64_t row_tiles = (n + 31) / 32;
+  if (row_tiles > 0x7FFFFFFF) {
+    set_last_error("copy_strided: too many rows");
+    return kBadShape;
+  }
+  copy_strided_kernel<<<dim3((unsigned)row_tiles, (unsigned)((k + 31) / 32)), 256, 0, stream>>>(src, srs, scs, dst, drs,
+                                                                                                 dcs, n, k);
+  PBL_LAUNCH_CHECK();
+  return kOk;
+}
+
 }  // namespace pbl

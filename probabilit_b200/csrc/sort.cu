@@ -758,15 +758,19 @@ int launch_pass_cfg(const PassArgs& a, int ncols, cudaStream_t stream) {
   return launch_pass<256, 16, 3, SCATTER>(a, ncols, stream);
 }
 
-// PBL_PASS_IMPL=classic selects the one-tile-per-block kernel above (kept for A/B measurements and for
-// the no-look-back debug path); the default is the persistent bulk-async kernel (pass_tma.cuh)
-bool pass_impl_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PBL_PASS_IMPL");
-    v = (e && e[0] == 'c') ? 0 : 1;
-  }
-  return v == 1;
+// Which digit-pass kernel a launch of `ncols` columns of n rows uses.  The persistent bulk-async kernel
+// (pass_tma.cuh) everywhere, except for launches on one or two LONG columns (the multi-GPU driver's shape at
+// 4+ GPUs, weak scaling): there all tiles in flight share one look-back chain, the ticket taken a tile ahead buys
+// nothing, and the one-tile-per-block kernel above is the faster one (8 GPUs, 8e8-row columns: 5.97 vs 6.35 ms
+// per pass, profiles/r1_bench_n8.json vs r2_bench_n8_weak.json; one GPU, same shape: 125.5 vs 127.4 ms per
+// rank_scores).  PBL_PASS_IMPL=classic|tma forces one (A/B measurements; "classic" also serves the
+// no-look-back debug path); PBL_PASS_CLASSIC_ABOVE=<rows> moves the switch-over.
+bool pass_impl_tma(uint32_t n, int ncols) {
+  const char* e = getenv("PBL_PASS_IMPL");  // (read per call: the parity tests switch it between plans)
+  if (e && e[0]) return e[0] != 'c';
+  uint64_t above = 300000000ull;
+  if (const char* a = getenv("PBL_PASS_CLASSIC_ABOVE")) above = strtoull(a, nullptr, 10);
+  return !(ncols <= 2 && n > above && n <= kMaxSortNClassic);
 }
 
 }  // namespace
@@ -883,7 +887,7 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
                      int ncols, int window_bits, const SortBuffers& buf, bool use_lookback,
                      cudaStream_t stream) {
   if (n == 0 || ncols <= 0) return kOk;
-  if (n > kMaxSortN || (n > kMaxSortNClassic && !(use_lookback && pass_impl_tma()))) {
+  if (n > kMaxSortN || (n > kMaxSortNClassic && !(use_lookback && pass_impl_tma(n, ncols)))) {
     set_last_error("sort_columns_f64: n exceeds 2^31-1 rows per column (2^30-1 with PBL_PASS_IMPL=classic)");
     return kBadShape;
   }
@@ -944,12 +948,13 @@ int sort_columns_f64(const double* in, int64_t row_stride, int64_t col_stride, u
   a.window_bits = window_bits;
   a.ntiles = ntiles;
   a.use_lookback = use_lookback ? 1 : 0;
-  const bool tma = use_lookback && pass_impl_tma();
+  const bool tma = use_lookback && pass_impl_tma(n, ncols);
   for (int pass = 0; pass < npasses; ++pass) {
     if (tma) {
       // epoch-tagged look-back words: nothing to clear
     } else if (use_lookback) {
-      PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, status_bytes, stream));
+      // the one-tile-per-block pass keeps 32-bit words [ncols][ntiles][256]: clear those, not the whole allocation
+      PBL_CUDA_CHECK(cudaMemsetAsync(buf.status, 0, std::min(status_bytes, (size_t)ncols * ntiles * kRadix * 4), stream));
     } else {
       tile_hist_kernel<256><<<dim3(ntiles, ncols), 256, 0, stream>>>(
           in, row_stride, col_stride, buf.keysA, buf.keysB, buf.status, buf.plan, buf.kminmax,

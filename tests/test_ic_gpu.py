@@ -62,17 +62,21 @@ def test_random_problems_bit_exact(monkeypatch, n, k, seed, lookback):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("n,k,seed,ties", [(300_001, 3, 11, False), (1_200_000, 2, 12, False), (500_000, 3, 13, True)])
+@pytest.mark.parametrize("n,k,seed,ties", [(300_001, 3, 11, False), (1_200_000, 2, 12, False), (500_000, 3, 13, True),
+                                           (700_000, 2, 14, True)])
 def test_one_tile_per_block_consumer_is_bit_exact(monkeypatch, n, k, seed, ties):
     """Columns longer than PBL_POST_CLASSIC_ABOVE rows (default 3e8: the multi-GPU shapes) are finished by
-    post_sort_kernel instead of the persistent post_tma_kernel (ic.cu: post_impl_tma); forced here on small
-    columns, and via the row threshold, so that the path the 8-GPU runs take is pinned against the oracle."""
+    post_sort_kernel instead of the persistent post_tma_kernel (ic.cu: post_impl_tma), and launches on one or two
+    such columns use the one-tile-per-block digit pass (sort.cu: pass_impl_tma); forced here on small columns,
+    and via the row thresholds, so that the path the 8-GPU runs take is pinned against the oracle."""
     from probabilit_b200 import ImanConover
 
     if ties:
         monkeypatch.setenv("PBL_POST_CLASSIC_ABOVE", "1000")
+        monkeypatch.setenv("PBL_PASS_CLASSIC_ABOVE", "1000")  # (k <= 2 columns per launch only)
     else:
         monkeypatch.setenv("PBL_POST_IMPL", "classic")
+        monkeypatch.setenv("PBL_PASS_IMPL", "classic")
     rng = np.random.default_rng(seed)
     X = rng.normal(size=(n, k)) * rng.lognormal(size=k) + rng.normal(size=k)
     if ties:
