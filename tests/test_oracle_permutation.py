@@ -75,3 +75,23 @@ def test_numpy_pairwise_sum_restatement():
     for n in list(range(1, 40)) + [127, 128, 129, 190, 255, 256, 1000, 4095, 5000]:
         a = rng.normal(size=n) * 10.0 ** rng.integers(-3, 3, size=n)
         assert pairwise(a) == float(np.sum(a)), n
+
+
+def test_swap_generator_snapshot_restore_replays_the_same_draws():
+    """PermutationCorrelator replays the swap stream after an early stop (reference correlation.py:668-703 leaves
+    the generator where the loop stopped): the product's host-side generator is rewound with snapshot() /
+    restore() instead of a deep copy of its 8 N byte permutation -- same draws, including across a redraw."""
+    from probabilit_b200.correlation import SwapIndexGenerator
+
+    gen = SwapIndexGenerator(np.random.default_rng(3), 41)
+    for _ in range(3):
+        gen(5)
+    snap = gen.snapshot()
+    first = [gen(6) for _ in range(7)]  # 7 x 12 indices > 41: crosses at least one redraw
+    after = gen.rng.random()
+    gen.restore(snap)
+    again = [gen(6) for _ in range(7)]
+    for (a0, a1), (b0, b1) in zip(first, again):
+        np.testing.assert_array_equal(a0, b0)
+        np.testing.assert_array_equal(a1, b1)
+    assert gen.rng.random() == after
