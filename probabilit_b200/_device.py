@@ -96,6 +96,12 @@ def as_device_columns(q):
                 qc = q.t().contiguous().t()
                 return as_device_columns(qc)
             raise TypeError("device quantiles must be column-major (strides (1, n) elements)")
+        # the library's graph / correlator entry points run on the default stream: whatever produced this
+        # memory on the caller's current stream (torch: possibly a non-default one) must have finished
+        if type(q).__module__.startswith("torch"):
+            import torch
+
+            torch.cuda.current_stream(q.device).synchronize()
         view = DeviceColumns.__new__(DeviceColumns)
         view.lib = _lib.require_gpu()
         view.n, view.k, view.nbytes = int(n), int(k), int(n) * int(k) * 8
