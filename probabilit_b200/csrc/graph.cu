@@ -917,7 +917,7 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
   if (!row_inputs.empty()) memcpy(host.data() + off_rows, row_inputs.data(), row_inputs.size() * 4);
   static std::mutex mu;
   static std::map<int, std::pair<unsigned char*, size_t>> staging;  // per device
-  static bool attr_set[2] = {false, false};
+  static std::map<int, int> attr_set;  // per device: bit 0 = R 2, bit 1 = R 4 (the attribute is per context)
   std::lock_guard<std::mutex> lock(mu);
   int device = 0;
   PBL_CUDA_CHECK(cudaGetDevice(&device));
@@ -943,12 +943,13 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
   a.first_nonfinite = reinterpret_cast<int*>(dev);
   a.row_inputs = reinterpret_cast<const int32_t*>(dev + off_rows);
   a.n_row_inputs = (int)row_inputs.size();
-  if (!attr_set[R == 4]) {
+  const int attr_bit = R == 4 ? 2 : 1;
+  if (!(attr_set[device] & attr_bit)) {
     if (R == 4)
       PBL_CUDA_CHECK(cudaFuncSetAttribute(pbl::graph_eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
     else
       PBL_CUDA_CHECK(cudaFuncSetAttribute(pbl::graph_eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
-    attr_set[R == 4] = true;
+    attr_set[device] |= attr_bit;
   }
   const int64_t per_block = (int64_t)pbl::kGraphBlockR * R;
   const int64_t blocks_needed = (n + 1 + per_block - 1) / per_block;
