@@ -1270,8 +1270,9 @@ int ic_plan_set_target(IcPlan* p, const double* P_lower_host) {
 static SortBuffers sort_view(const IcPlan* p) { return p->sort; }
 
 template <int MODE>
+// c: global index of the batch's first column; the launch covers the batch-local columns [j0, j0 + nb)
 static int launch_post_tma(IcPlan* p, int c, int nb, int shift, uint32_t epoch, uint32_t* counter,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int j0 = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     PBL_CUDA_CHECK(cudaFuncSetAttribute(post_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1279,22 +1280,23 @@ static int launch_post_tma(IcPlan* p, int c, int nb, int shift, uint32_t epoch, 
     attr_set = true;
   }
   PostArgs a;
-  a.keysA = p->sort.keysA;
-  a.keysB = p->sort.keysB;
-  a.valsA = p->sort.valsA;
-  a.valsB = p->sort.valsB;
-  a.plan = p->sort.plan;
-  a.maps = p->sort.maps;
-  a.sortedX = p->sortedX + (size_t)c * p->n;
+  const size_t off = (size_t)j0 * p->n;
+  a.keysA = p->sort.keysA + off;
+  a.keysB = p->sort.keysB + off;
+  a.valsA = p->sort.valsA + off;
+  a.valsB = p->sort.valsB + off;
+  a.plan = p->sort.plan + j0;
+  a.maps = p->sort.maps + j0;
+  a.sortedX = p->sortedX + (size_t)(c + j0) * p->n;
   a.vdw = p->vdw;
   a.flags = p->flags;
-  a.status64 = reinterpret_cast<uint64_t*>(p->sort.status);
   a.ticket = counter;
   a.n = (uint32_t)p->n;
   a.ntiles = (uint32_t)((p->n + kTile - 1) / kTile);
+  a.status64 = reinterpret_cast<uint64_t*>(p->sort.status) + (size_t)j0 * a.ntiles * kRadix;
   a.total_tiles = a.ntiles * (uint32_t)nb;
   a.epoch = epoch;
-  a.col_base = c;
+  a.col_base = c + j0;
   a.part_shift = shift;
   a.ncols = (uint32_t)nb;
   a.ncols_interleave = tickets_interleaved() ? std::min<uint32_t>((uint32_t)nb, kInterleaveWidth) : 0u;
@@ -1477,7 +1479,15 @@ int ic_stage_rank_gather(IcPlan* p, double* Y, int64_t row_stride, int64_t col_s
     PBL_RETURN_IF(scatter_prepare(n, nb, sort_view(p), row_stride, p->use_lookback, kPostTile, &shift, &ntiles,
                                   &counter, &epoch, stream));
     if (p->use_lookback && post_impl_tma(n)) {
-      PBL_RETURN_IF(launch_post_tma<1>(p, c, nb, shift, epoch, counter, stream));
+      // Batches of 2 .. 7 columns go column by column: with so few columns interleaved the gather-mode consumer,
+      // whose tiles are short, spends most of its time polling look-back words (ncu, 1e8 x 2: 2.1x the
+      // instructions and 5.4 ms in one launch against 1.0 + 1.4 ms in two; 3 / 4 columns: +0.8 / +0.6 ms per
+      // column); from ~8 columns on the interleave wins (15 columns: 1.2 ms per column).
+      if (nb > 1 && nb < 8) {
+        for (int j = 0; j < nb; ++j) PBL_RETURN_IF(launch_post_tma<1>(p, c, 1, shift, epoch, counter, stream, j));
+      } else {
+        PBL_RETURN_IF(launch_post_tma<1>(p, c, nb, shift, epoch, counter, stream));
+      }
     } else {
       post_sort_kernel<1><<<grid, kPostBlock, kPostSmem, stream>>>(
           p->sort.keysA, p->sort.keysB, p->sort.valsA, p->sort.valsB, p->sort.plan, p->sort.kminmax,
