@@ -171,3 +171,75 @@ def test_device_form_chains_the_mutual_fund_graph_through_the_accumulator(monkey
     # 20 x (ppf -> MUL via the accumulator -> ADD via the accumulator); only the running total lives in a slot
     assert acc >= 40 and no_write >= 40, (acc, no_write, len(ops), [hex(o) for o in ops])
     assert seen["abi_slots"] >= 20 and seen["n_slots"] <= 2, (seen["abi_slots"], seen["n_slots"])
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_device_form_on_random_graphs(seed, monkeypatch):
+    """Random modeling graphs (inverse CDFs with immediate and node-valued parameters, arithmetic, comparisons,
+    shared sub-expressions, all nodes retained or only the sink): the VM run on the ABI program and on the
+    library's device form of it (producers sunk, accumulator operands, slots re-allocated) must agree on every
+    retained node, bit for bit."""
+    import probabilit_b200.modeling as m
+
+    rng = np.random.default_rng(1000 + seed)
+
+    def build():
+        r = np.random.default_rng(2000 + seed)  # the same graph both times
+        nodes = []
+        for _ in range(int(r.integers(2, 6))):
+            kind = r.choice(["norm", "uniform", "expon", "triang"])
+            if kind == "norm":
+                nodes.append(m.Distribution("norm", loc=float(r.normal()), scale=float(r.uniform(0.5, 2))))
+            elif kind == "uniform":
+                nodes.append(m.Distribution("uniform", loc=float(r.normal()), scale=float(r.uniform(0.5, 2))))
+            elif kind == "expon":
+                nodes.append(m.Distribution("expon", scale=float(r.uniform(0.5, 2))))
+            else:
+                nodes.append(m.Distribution("triang", c=float(r.uniform(0.1, 0.9)), loc=0.0, scale=float(r.uniform(1, 3))))
+        if r.random() < 0.5:  # a composite distribution: its scale is another node's value
+            nodes.append(m.Distribution("norm", loc=0.0, scale=m.Abs(nodes[0]) + 0.5))
+        for _ in range(int(r.integers(4, 14))):
+            a = nodes[int(r.integers(len(nodes)))]
+            b = nodes[int(r.integers(len(nodes)))] if r.random() < 0.7 else float(r.normal())
+            op = r.choice(["add", "mul", "sub", "gt", "neg", "abs", "max", "square"])
+            if op == "add":
+                nodes.append(a + b)
+            elif op == "mul":
+                nodes.append(a * b)
+            elif op == "sub":
+                nodes.append(b - a)
+            elif op == "gt":
+                nodes.append((a > b) * 1.0)  # (booleans only feed float arithmetic: bool ** 2 etc. is int64 in NumPy)
+            elif op == "neg":
+                nodes.append(-a)
+            elif op == "abs":
+                nodes.append(m.Abs(a))
+            elif op == "max":
+                nodes.append(m.Max(a, b))
+            else:
+                nodes.append(a ** 2)
+        sink = nodes[-1]
+        for extra in nodes[-4:-1]:
+            sink = sink + extra
+        return sink
+
+    fake_device.install(monkeypatch)
+    results = []
+    for device_form in (False, True):
+        monkeypatch.setattr(fake_device, "DEVICE_FORM", device_form)
+        sink = build()
+        d = sink.num_distribution_nodes()
+        q = np.random.default_rng(3000 + seed).random((48, d))
+        gc = [] if seed % 2 else None
+        sink.sample_from_quantiles(q, gc_strategy=gc)
+        G = sink.to_graph()
+        import networkx as nx
+
+        order = list(nx.topological_sort(G))
+        results.append([np.array(n.samples_) if getattr(n, "samples_", None) is not None else None
+                        for n in sorted(order, key=lambda n: n._id)])
+    assert len(results[0]) == len(results[1])
+    for a, b in zip(*results):
+        assert (a is None) == (b is None)
+        if a is not None:
+            np.testing.assert_array_equal(a, b)
