@@ -82,3 +82,30 @@ def test_infinite_iterations_stop_on_tolerance():
     got = pc(X)
     np.testing.assert_array_equal(got, want)
     assert pc._error(np.corrcoef(got, rowvar=False), Ct) < 0.02
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (7, 3), (1000, 8), (4097, 33), (65, 70)])
+@pytest.mark.parametrize("src_order,dst_order", [("F", "C"), ("C", "F"), ("C", "C"), ("F", "F")])
+def test_strided_copy_converts_between_layouts(n, k, src_order, dst_order):
+    """pbl_copy_strided_f64: the device-side layout conversion around the correlators that work column-major
+    inside (the result of PermutationCorrelator goes back in C order like the reference's X.copy(),
+    correlation.py:830-831), against NumPy on every pair of layouts, tile-edge shapes included."""
+    import ctypes as C
+
+    import gpu_util
+    from probabilit_b200 import _lib
+
+    lib = _lib.require_gpu()
+    rng = np.random.default_rng(n * 100 + k)
+    A = np.asarray(rng.normal(size=(n, k)), order=src_order)
+    src = gpu_util.DeviceArray(A)
+    dst = gpu_util.DeviceArray(np.zeros((n, k), order=dst_order))
+    srs, scs = (A.strides[0] // 8, A.strides[1] // 8)
+    drs, dcs = ((k, 1) if dst_order == "C" else (1, n))
+    _lib.check(lib.pbl_copy_strided_f64(src.ptr, srs, scs, dst.ptr, drs, dcs, n, k, None), "pbl_copy_strided_f64")
+    out = np.empty((n, k), order=dst_order)
+    _lib.check(lib.pbl_memcpy_d2h(out.ctypes.data, dst.ptr, out.nbytes, None))
+    _lib.check(lib.pbl_stream_synchronize(None))
+    np.testing.assert_array_equal(out, A)
+    src.free()
+    dst.free()
