@@ -887,7 +887,9 @@ int pbl_graph_eval_f64(const pbl_graph_instr* program, int32_t n_instr, int32_t 
   if (const char* e = getenv("PBL_GRAPH_ROWS")) R = atoi(e) == 2 ? 2 : (atoi(e) == 4 && 2 * slot_bytes2 <= 200 * 1024 ? 4 : R);
   const size_t slot_bytes = slot_bytes2 * (size_t)(R / 2);
   const size_t kSmemCap = 227 * 1024;
-  const int prog_in_smem = slot_bytes + prog_bytes <= kSmemCap ? 1 : 0;
+  // (PBL_GRAPH_PROGRAM=global forces the decode-from-global path, for the parity tests)
+  const char* prog_env = getenv("PBL_GRAPH_PROGRAM");
+  const int prog_in_smem = (slot_bytes + prog_bytes <= kSmemCap && !(prog_env && prog_env[0] == 'g')) ? 1 : 0;
   const size_t smem = slot_bytes + (prog_in_smem ? prog_bytes : 0);
   if (smem > kSmemCap) {
     pbl::set_last_error("pbl_graph_eval_f64: " + std::to_string(n_slots) + " live values per sample do not fit the kernel's shared memory");

@@ -267,3 +267,29 @@ def test_large_graph_in_one_launch():
     out = s.sample(2_000_000, random_state=1, gc_strategy=[])
     assert _lib.kernel_launches() - before == 1
     assert abs(out.mean() / 76583.6 - 1) < 0.01
+
+
+@pytest.mark.parametrize("rows,program", [("2", ""), ("4", ""), ("4", "global"), ("2", "global")])
+def test_kernel_variants_agree(monkeypatch, rows, program):
+    """graph_eval_kernel<2> / <4> (rows per thread, chosen by the shared-memory budget) and the decode-from-global
+    path (programs that do not fit beside the slots) are selected by size; forced here on a small graph: all of
+    them must give the values of the default configuration, bit for bit -- in-kernel Philox, supplied quantiles,
+    an odd number of rows (pairs straddle the end) and all nodes retained."""
+    import probabilit_b200.modeling as m
+
+    def run():
+        s, named = graph_recipes.mutual_fund(m)
+        a = s.sample(100_001, random_state=3)  # all nodes retained, odd n
+        kept = [np.array(node.samples_) for _, node in named]
+        s2, _ = graph_recipes.mutual_fund(m)
+        q = np.random.default_rng(5).random((4097, 20))
+        b = s2.sample_from_quantiles(q, gc_strategy=[])
+        return [np.array(a), np.array(b)] + kept
+
+    want = run()
+    monkeypatch.setenv("PBL_GRAPH_ROWS", rows)
+    if program:
+        monkeypatch.setenv("PBL_GRAPH_PROGRAM", program)
+    got = run()
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
